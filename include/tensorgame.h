@@ -1,0 +1,97 @@
+/*
+ * tensorgame.h -- C ABI of libtensorgame_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the data-parallel hot path of kurtosis/mat_mul's
+ * TensorGame environment.  The reference has no FFI: its boundary is the
+ * Python surface of utils.py / datasets.py / act.py.  Each entry point below
+ * names the reference code it replaces (file:line in /root/reference); the
+ * Python mirrors in mat_mul_b200/{utils,datasets,act}.py bind them with
+ * ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.
+ *   - unless the name ends in _host, every pointer is a CUDA DEVICE pointer
+ *     owned by the caller; calls are asynchronous on `stream` (a cudaStream_t
+ *     passed as void*), never allocate and never synchronise.
+ *   - *_host entry points take HOST pointers (pinned for full speed), move the
+ *     data themselves through a caller-created tg_host_ctx and return after
+ *     the results are in host memory.
+ *   - return value: 0 on success, a negative TG_E_* code otherwise; nothing
+ *     throws.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point returns TG_E_CUDA.
+ *
+ * Device formats (S = dim_3d in {4, 9, 16}; see DESIGN.md "Data layout")
+ *   slab   int8  [B][GP]   residual tensors, entry (i,j,k) at i*RP + j*S + k,
+ *                          RP = roundup4(S*S), GP = roundup16(S*RP); padding
+ *                          bytes are zero.  (S=4: 16/64, S=9: 84/768,
+ *                          S=16: 256/4096.)  Values must stay in [-64, 63]
+ *                          for the next step to be guaranteed (TG_FLAG_RANGE).
+ *   tape   uint8 [B][TP]   action tokens cat(u,v,w)+shift in bytes [0,3S),
+ *                          TP = roundup16(3S) (16/32/48), padding zero.
+ *   flags  uint8 [B]       TG_FLAG_* bits per game.
+ *   nnz    int32 [B]       count of non-zero residual entries (rank upper
+ *                          bound, training.py:259-266).
+ */
+#ifndef TENSORGAME_H
+#define TENSORGAME_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_VERSION 100
+
+#define TG_OK 0
+#define TG_E_ARG (-1)     /* bad argument (unsupported S, null pointer, misaligned buffer) */
+#define TG_E_CUDA (-2)    /* CUDA runtime error; tg_last_cuda_error() has the code */
+#define TG_E_RANGE (-3)   /* value does not fit the device format */
+
+#define TG_FLAG_TERMINAL 1u /* new head all zero: utils.py:181-188 on the head (act.py:177) */
+#define TG_FLAG_NULL 2u     /* rank-1 update all zero: utils.py:191-194 */
+#define TG_FLAG_RANGE 4u    /* a residual entry left [-64, 63]: int8 slab no longer guaranteed */
+
+int tg_version(void);
+int tg_last_cuda_error(void);
+const char *tg_error_string(int code);
+
+/* geometry of the device formats for a given S; returns TG_E_ARG for unsupported S */
+int tg_layout(int S, int *row_pitch, int *game_pitch, int *token_pitch);
+
+/* ---- boundary conversions (reference dtypes <-> device formats) ---------- */
+/* float32 residuals, game b at src + b*src_stride (elements), dense (S,S,S)
+ * -> slab.  range_flag (device int32, may be NULL) is OR-ed with 1 if a value
+ * is non-integral or outside [-128,127].  Replaces the float32 state tensors
+ * of utils.py:99-111 / datasets.py:94-114 at the boundary. */
+int tg_pack_f32(const float *src, int64_t src_stride, int8_t *slab, int64_t B, int S, int32_t *range_flag, void *stream);
+/* slab -> float32 dense (S,S,S) at dst + b*dst_stride: the state the model
+ * consumes (model.py:101-103). */
+int tg_expand_f32(const int8_t *slab, float *dst, int64_t dst_stride, int64_t B, int S, void *stream);
+/* int64 tokens (B,3S) (reference action format, utils.py:56-66) <-> tape */
+int tg_pack_actions_i64(const int64_t *actions, uint8_t *tape, int64_t B, int S, int32_t *range_flag, void *stream);
+int tg_unpack_actions_i64(const uint8_t *tape, int64_t *actions, int64_t B, int S, void *stream);
+
+/* ---- K1: batched transition --------------------------------------------- */
+/* slab_out[b] = slab_in[b] - u(x)v(x)w of tape[b] with coefficient = token -
+ * shift; flags/nnz per game.  In place (slab_out == slab_in) is allowed.
+ * Replaces act.py:266-275 (get_child_states), training.py:253-267
+ * (_take_action arithmetic), utils.py:181-188 (tensor_factorized on the head),
+ * utils.py:191-194 (remove_null_actions), utils.py:69-96.  shift in [1,4]. */
+int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz,
+            int64_t B, int S, int shift, void *stream);
+
+/* ---- host-buffer path (end-to-end through PCIe) -------------------------- */
+typedef struct tg_host_ctx tg_host_ctx;
+/* creates streams and device staging for chunks of up to max_chunk games */
+int tg_host_ctx_create(tg_host_ctx **ctx, int device, int S, int64_t max_chunk);
+int tg_host_ctx_destroy(tg_host_ctx *ctx);
+/* same contract as tg_step with HOST slabs/tapes/flags/nnz; chunks are
+ * pipelined H2D -> kernel -> D2H over three streams; returns when done. */
+int tg_step_host(tg_host_ctx *ctx, const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags,
+                 int32_t *nnz, int64_t B, int shift);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSORGAME_H */

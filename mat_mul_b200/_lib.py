@@ -1,0 +1,116 @@
+"""Loader for libtensorgame_b200.so (the C-ABI CUDA library, include/tensorgame.h).
+
+The library is built in-tree with nvcc for sm_100a only.  There is no CPU
+fallback: if the library cannot be loaded, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB_PATH = PKG / "libtensorgame_b200.so"
+HEADER = PKG.parent / "include" / "tensorgame.h"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+TG_OK = 0
+FLAG_TERMINAL = 1
+FLAG_NULL = 2
+FLAG_RANGE = 4
+
+
+class TensorGameError(RuntimeError):
+    pass
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HEADER]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mat_mul_b200/libtensorgame_b200.so"""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, sources())]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise TensorGameError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_i8p = C.c_void_p
+_vp = C.c_void_p
+
+_SIGNATURES = {
+    "tg_version": (C.c_int, []),
+    "tg_last_cuda_error": (C.c_int, []),
+    "tg_error_string": (C.c_char_p, [C.c_int]),
+    "tg_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tg_pack_f32": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp]),
+    "tg_expand_f32": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp]),
+    "tg_pack_actions_i64": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vp]),
+    "tg_unpack_actions_i64": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "tg_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
+    "tg_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64]),
+    "tg_host_ctx_destroy": (C.c_int, [_vp]),
+    "tg_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
+    "tg_tune_step_ctas_per_sm": (C.c_int, [C.c_int]),
+}
+
+
+def exported_symbols() -> list[str]:
+    """Every function include/tensorgame.h declares (used by the symbol test)."""
+    import re
+
+    text = HEADER.read_text()
+    return sorted(set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if _stale():
+            try:
+                build()
+            except (TensorGameError, FileNotFoundError) as e:
+                if not LIB_PATH.exists():
+                    raise TensorGameError(
+                        "libtensorgame_b200.so is missing and could not be built; "
+                        "run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)"
+                    ) from e
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != TG_OK:
+        L = lib()
+        msg = L.tg_error_string(code).decode()
+        extra = f" (cudaError {L.tg_last_cuda_error()})" if code == -2 else ""
+        raise TensorGameError(f"{what}: {msg}{extra}")

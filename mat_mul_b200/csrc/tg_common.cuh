@@ -1,0 +1,97 @@
+// tg_common.cuh -- shared device helpers for the TensorGame kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tensorgame.h"
+
+namespace tg {
+
+// ---------------------------------------------------------------- geometry
+// Device slab: int8 [B][GP]; entry (i,j,k) at i*RP + j*S + k.  One 32-bit word
+// holds four consecutive (j,k) entries of one i-row, so the rank-1 update of a
+// word is  u_i * pack(v_j w_k)  -- one IMAD per word (see tg_step.cu).
+template <int S>
+struct Geo {
+    static constexpr int S2 = S * S;
+    static constexpr int S3 = S2 * S;
+    static constexpr int RP = (S2 + 3) & ~3;       // row pitch (bytes)
+    static constexpr int WR = RP / 4;              // 32-bit words per row
+    static constexpr int GP = (S * RP + 15) & ~15; // game pitch (bytes)
+    static constexpr int TP = (3 * S + 15) & ~15;  // token pitch (bytes)
+    static constexpr bool STRADDLE = (S % 4) != 0; // a word can span two j
+};
+
+__host__ __device__ constexpr bool supported_S(int S) { return S == 4 || S == 9 || S == 16; }
+
+extern int g_last_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return TG_E_CUDA;
+}
+#define TG_CUDA(call)                                  \
+    do {                                               \
+        cudaError_t _e = (call);                       \
+        if (_e != cudaSuccess) return tg::cuda_fail(_e); \
+    } while (0)
+
+// ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA 1-D)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted on the mbarrier (UBLKCP in SASS)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (bulk store source)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- SWAR helpers on 4 packed int8
+constexpr uint32_t H4 = 0x80808080u;
+constexpr uint32_t ONES4 = 0x01010101u;
+
+// bit 7 of each byte set iff that byte is non-zero
+__device__ __forceinline__ uint32_t nonzero_mask(uint32_t x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & H4; }
+
+// sum of the four unsigned bytes of x
+__device__ __forceinline__ uint32_t byte_sum(uint32_t x) { return __dp4a(x, ONES4, 0u); }
+
+} // namespace tg
