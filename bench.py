@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: env steps/s of the batched TensorGame transition.
+
+Workload (BASELINE.json configs[1]): 3x3 matmul tensor (9x9x9), 2^20 parallel
+games per GPU, coefficients {-2..2}.  One "step" = one tg_step launch over the
+whole batch (every game makes one transition).  See DESIGN.md "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  For N>1 launch with torch.distributed.run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ALGO_BYTES = {4: 145, 9: 1490, 16: 8245}  # 2*S^3 + 3S + 1 + 4 per env step
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def parse() -> argparse.Namespace:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=9, choices=[4, 9, 16], help="dim_3d S")
+    ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning sweep only")
+    ap.add_argument("--variant", type=int, default=0, help="tuning sweep only")
+    return ap.parse_args()
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(S: int, shift: int, seconds: float = 12.0):
+    """The reference's CPU path for the same workload: the oracle's C port of
+    training.py:253-266 on the reference's dtypes (float32 residuals, int64
+    tokens), threaded over games with every host core.  Bounded sample."""
+    import numpy as np
+
+    from oracle import tg_oracle as orc
+
+    cores = orc.num_threads()
+    Bs = 1 << 16
+    rng = np.random.default_rng(0)
+    T = (rng.integers(-2, 3, (Bs, S, S, S)) * (rng.random((Bs, S, S, S)) < 0.3)).astype(np.float32)
+    tok = rng.integers(0, 2 * shift + 1, (Bs, 3 * S)).astype(np.int64)
+    tok[rng.random((Bs, 3 * S)) < 0.6] = shift
+    out = np.empty_like(T); flags = np.empty(Bs, np.uint8); nnz = np.empty(Bs, np.int32)
+    orc.step_batch_f32(T, tok, shift, out, flags, nnz)  # warm
+    t0 = time.perf_counter()
+    orc.step_batch_f32(T, tok, shift, out, flags, nnz)
+    one = time.perf_counter() - t0
+    reps = max(1, min(400, int(seconds / max(one, 1e-6))))
+    return cores, Bs, reps, T, tok, out, flags, nnz
+
+
+def run_reference(args) -> None:
+    """--impl reference: rank 0 times the CPU port; other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np  # noqa: F401
+
+    from oracle import tg_oracle as orc
+
+    S, shift = args.size, 2
+    cores, Bs, reps, T, tok, out, flags, nnz = cpu_reference_leg(S, shift, seconds=3.0)
+    per_step_reps = max(1, reps // 4)  # one bench "step" = per_step_reps passes over the 65536-game sample
+    for _ in range(args.warmup):
+        orc.step_batch_f32(T, tok, shift, out, flags, nnz)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step_reps):
+            orc.step_batch_f32(T, tok, shift, out, flags, nnz)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step_reps * Bs / dt
+    sample = f"{per_step_reps} passes over {Bs} games of {S}x{S}x{S} per step (float32 residuals, int64 tokens), OpenMP over games"
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"tensorgame step {S}x{S}x{S}, coefficients -2..2 (CPU port of training.py:253-266)",
+                   "games_per_gpu": args.games, "size": S},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mat_mul_b200 import _lib, env
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, shift, B, K, W = args.size, 2, args.games, args.steps, max(args.warmup, 3)
+    lay = env.layout(S)
+    if args.ctas_per_sm:
+        _lib.lib().tg_tune_step_ctas_per_sm(args.ctas_per_sm)
+    if args.variant:
+        _lib.lib().tg_tune_step_variant(args.variant)
+
+    # ---- synthetic games, resident in HBM: sparse residuals in [-2,2], tokens with P(coef=0)=0.7
+    gen = torch.Generator(device=dev).manual_seed(0x5EED + rank)
+    dense = torch.randint(-2, 3, (B, S, S, S), device=dev, generator=gen, dtype=torch.int8)
+    dense *= (torch.rand((B, S, S, S), device=dev, generator=gen) < 0.3)
+    slab_a = env.new_slab(B, S, dev)
+    env.slab_view(slab_a, S).copy_(dense)
+    del dense
+    slab_b = torch.empty_like(slab_a)
+    n_tapes = 4
+    tapes = []
+    for _ in range(n_tapes):
+        tk = torch.randint(0, 5, (B, 3 * S), device=dev, generator=gen)
+        tk[torch.rand((B, 3 * S), device=dev, generator=gen) < 0.625] = shift  # P(0) = 0.7
+        tapes.append(env.pack_actions(tk, S))
+        del tk
+    flags = torch.empty(B, dtype=torch.uint8, device=dev)
+    nnz = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def one_step(i: int) -> None:
+        src, dst = (slab_a, slab_b) if i % 2 == 0 else (slab_b, slab_a)
+        env.step_batch(src, tapes[i % n_tapes], S, shift, out=dst, flags=flags, nnz=nnz)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        one_step(W + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # keep the sampler alive long enough to see the load even for very short timed regions
+    t_end = time.perf_counter() + max(0.0, 1.0 - ms / 1e3)
+    i = 0
+    while time.perf_counter() < t_end:
+        one_step(i); i += 1
+        if i % 8 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end through the C ABI with HOST buffers (tg_step_host): PCIe in + kernel + PCIe out
+    e2e = None
+    if not args.no_e2e:
+        Be = B
+        h_slab = torch.empty((Be, lay.game_pitch), dtype=torch.int8).pin_memory()
+        h_slab.copy_(slab_a[:Be])
+        h_tape = torch.empty((Be, lay.token_pitch), dtype=torch.uint8).pin_memory()
+        h_tape.copy_(tapes[0][:Be])
+        h_out = torch.empty_like(h_slab).pin_memory()
+        h_flags = torch.empty(Be, dtype=torch.uint8).pin_memory()
+        h_nnz = torch.empty(Be, dtype=torch.int32).pin_memory()
+        hs = env.HostStepper(S, local, chunk=1 << 16)
+        Ke = max(3, min(K, 10))
+        for _ in range(2):
+            hs.step(h_slab, h_tape, h_out, h_flags, h_nnz, shift)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            hs.step(h_slab, h_tape, h_out, h_flags, h_nnz, shift)  # returns with results in host memory
+        dt = time.perf_counter() - t0
+        hs.close()
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * Be * Ke / float(te.item()), "unit": "steps/s",
+               "h2d_bytes_per_step": Be * (lay.game_pitch + lay.token_pitch),
+               "d2h_bytes_per_step": Be * (lay.game_pitch + 5), "steps": Ke,
+               "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks over 3 streams)"}
+        del h_slab, h_tape, h_out
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        algo = ALGO_BYTES[S] * B
+        achieved = algo / (ms / K / 1e3) / 1e9
+        traffic = None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():
+            try:
+                traffic = json.loads(tj.read_text()).get(f"step_S{S}_B{B}")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+            "data": "synthetic",
+            "config": {"workload": f"tensorgame step {S}x{S}x{S}, 2^{B.bit_length() - 1} games per GPU, coefficients -2..2",
+                       "games_per_gpu": B, "size": S, "shift": shift, "sharding": f"game index, {world} rank(s), no data-path collective",
+                       "l2": f"inputs larger than L2 ({(2 * lay.game_pitch + lay.token_pitch) * B >> 20} MiB touched per step)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": "tg::step_kernel",
+                         "algorithmic_bytes_per_step": ALGO_BYTES[S],
+                         "moved_bytes_per_step": 2 * lay.game_pitch + lay.token_pitch + 5},
+            "e2e": e2e, "gpu_launches": K * world, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import tg_oracle as orc  # CPU baseline leg only (checker never on the product path)
+
+            cores, Bs, reps, T, tok, out, fl, nz = cpu_reference_leg(S, shift)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                orc.step_batch_f32(T, tok, shift, out, fl, nz)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": reps * Bs / dt, "unit": "steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{reps} passes over {Bs} games ({dt:.1f} s), C port of training.py:253-266 on float32/int64, OpenMP over games"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

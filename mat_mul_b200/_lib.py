@@ -77,6 +77,7 @@ _SIGNATURES = {
     "tg_host_ctx_destroy": (C.c_int, [_vp]),
     "tg_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
     "tg_tune_step_ctas_per_sm": (C.c_int, [C.c_int]),
+    "tg_tune_step_variant": (C.c_int, [C.c_int]),
 }
 
 

@@ -144,6 +144,7 @@ static int sm_count() {
 }
 
 static int g_step_ctas_per_sm = 0; // 0 = per-size default
+static int g_step_variant = 0;     // tuning sweeps only
 
 template <int S, int NT, int NPASS, int NSTAGE>
 static int launch_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz,
@@ -186,9 +187,13 @@ int tg_layout(int S, int *row_pitch, int *game_pitch, int *token_pitch) {
     return TG_OK;
 }
 
-// tuning knob for bench sweeps: resident CTAs per SM of the step kernel (0 = default)
+// tuning knobs for bench sweeps: CTAs launched per SM (0 = default) and kernel variant
 int tg_tune_step_ctas_per_sm(int n) {
     tg::g_step_ctas_per_sm = n;
+    return TG_OK;
+}
+int tg_tune_step_variant(int v) {
+    tg::g_step_variant = v;
     return TG_OK;
 }
 
@@ -200,9 +205,31 @@ int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_
     if (((uintptr_t)slab_in | (uintptr_t)slab_out | (uintptr_t)tape) & 15) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     switch (S) {
-    case 4: return tg::launch_step<4, 256, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 3, st);
-    case 9: return tg::launch_step<9, 256, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 3, st);
-    case 16: return tg::launch_step<16, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 3, st);
+    case 4:
+        switch (tg::g_step_variant) {
+        case 1: return tg::launch_step<4, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        case 2: return tg::launch_step<4, 256, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        case 3: return tg::launch_step<4, 256, 8, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        default: return tg::launch_step<4, 256, 4, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        }
+    case 9:
+        switch (tg::g_step_variant) {
+        case 1: return tg::launch_step<9, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
+        case 2: return tg::launch_step<9, 256, 1, 4>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
+        case 3: return tg::launch_step<9, 256, 4, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        case 4: return tg::launch_step<9, 512, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 3, st);
+        case 5: return tg::launch_step<9, 128, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 7, st);
+        case 6: return tg::launch_step<9, 128, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
+        case 7: return tg::launch_step<9, 256, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        default: return tg::launch_step<9, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        }
+    case 16:
+        switch (tg::g_step_variant) {
+        case 1: return tg::launch_step<16, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        case 2: return tg::launch_step<16, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        case 3: return tg::launch_step<16, 512, 1, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        default: return tg::launch_step<16, 256, 1, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+        }
     }
     return TG_E_ARG;
 }

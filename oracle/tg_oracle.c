@@ -186,6 +186,9 @@ void orc_step_batch(const int32_t *T_in, const int32_t *actions, int64_t B, int 
 /* The reference's own data types (float32 residuals, int64 tokens) for the
  * CPU baseline leg of bench.py: training.py:253-266 per game, threaded over
  * games.  Same arithmetic as orc_step. */
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
 void orc_step_batch_f32(const float *T_in, const int64_t *actions, int64_t B, int S, int shift,
                         float *T_out, uint8_t *flags, int32_t *nnz) {
     const int64_t S3 = (int64_t)S * S * S;
@@ -194,21 +197,29 @@ void orc_step_batch_f32(const float *T_in, const int64_t *actions, int64_t B, in
         const float *tin = T_in + b * S3;
         float *tout = T_out + b * S3;
         const int64_t *a = actions + b * 3 * S;
-        int n = 0, changed = 0;
+        float wf[64];
+        int unz = 0, vnz = 0, wnz = 0;
+        for (int k = 0; k < S; k++) {
+            wf[k] = (float)(a[2 * S + k] - shift);
+            unz |= (a[k] != shift), vnz |= (a[S + k] != shift), wnz |= (a[2 * S + k] != shift);
+        }
+        int n = 0;
         for (int i = 0; i < S; i++) {
-            int64_t ui = a[i] - shift;
+            const float ui = (float)(a[i] - shift);
             for (int j = 0; j < S; j++) {
-                int64_t uv = ui * (a[S + j] - shift);
+                const float uv = ui * (float)(a[S + j] - shift);
+                const float *ti = tin + (i * S + j) * S;
+                float *to = tout + (i * S + j) * S;
+                int nn = 0;
                 for (int k = 0; k < S; k++) {
-                    int64_t d = uv * (a[2 * S + k] - shift);
-                    float t = tin[(i * S + j) * S + k] - (float)d;
-                    changed |= (d != 0);
-                    n += (t != 0.f);
-                    tout[(i * S + j) * S + k] = t;
+                    const float t = ti[k] - uv * wf[k];
+                    nn += (t != 0.f);
+                    to[k] = t;
                 }
+                n += nn;
             }
         }
-        flags[b] = (uint8_t)((n == 0 ? ORC_FLAG_TERMINAL : 0u) | (changed ? 0u : ORC_FLAG_NULL));
+        flags[b] = (uint8_t)((n == 0 ? ORC_FLAG_TERMINAL : 0u) | ((unz && vnz && wnz) ? 0u : ORC_FLAG_NULL));
         nnz[b] = n;
     }
 }
