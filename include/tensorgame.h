@@ -51,6 +51,7 @@ extern "C" {
 #define TG_FLAG_TERMINAL 1u /* new head all zero: utils.py:181-188 on the head (act.py:177) */
 #define TG_FLAG_NULL 2u     /* rank-1 update all zero: utils.py:191-194 */
 #define TG_FLAG_RANGE 4u    /* a residual entry left [-64, 63]: int8 slab no longer guaranteed */
+#define TG_FLAG_EXHAUSTED 8u /* demo generation: a term hit max_tries and was forced to a unit triple */
 
 int tg_version(void);
 int tg_last_cuda_error(void);
@@ -80,6 +81,28 @@ int tg_unpack_actions_i64(const uint8_t *tape, int64_t *actions, int64_t B, int 
  * utils.py:191-194 (remove_null_actions), utils.py:69-96.  shift in [1,4]. */
 int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz,
             int64_t B, int S, int shift, void *stream);
+
+/* ---- K3: synthetic demonstrations ----------------------------------------- */
+/* Multi-step tapes are step-major: uint8 [R][N_total][TP]; `tape_step_stride`
+ * is the byte distance between consecutive steps (N_total*TP), so a rank can
+ * write its shard of demos straight into a larger tape.
+ *
+ * Throughput mode (device RNG; contract in DESIGN.md, restated by the oracle):
+ * demo d = first_demo + n draws its R factor triples from Philox4x32-10 keyed
+ * by (seed, d), 16-bit draws against the CDF of `probs` over `values` (HOST
+ * arrays, n_values <= 8, values in [-shift, shift]); a triple is rejected iff
+ * u, v or w is all zero (utils.py:229), at most max_tries tries per term
+ * (TG_FLAG_EXHAUSTED).  Writes tokens (values + shift) to the tape, the summed
+ * target tensors to slab [N][GP] and TG_FLAG_RANGE/EXHAUSTED to flags (may be
+ * NULL).  Replaces utils.py:203-233 and datasets.py:124-142 (different RNG
+ * stream than torch: see tg_demo_from_ustream for same-seed parity). */
+int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int S, int shift, const int8_t *values,
+                       const double *probs, int n_values, int max_tries, uint8_t *tape, int64_t tape_step_stride,
+                       int8_t *slab, uint8_t *flags, void *stream);
+/* slab[n] = sum_r rank1(tape[r][n]) -- the target tensor of a given action
+ * list (utils.py:40-53 uvw_to_demo, utils.py:232, datasets.py:141). */
+int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,
+                       uint8_t *flags, void *stream);
 
 /* ---- host-buffer path (end-to-end through PCIe) -------------------------- */
 typedef struct tg_host_ctx tg_host_ctx;

@@ -24,6 +24,7 @@ TG_OK = 0
 FLAG_TERMINAL = 1
 FLAG_NULL = 2
 FLAG_RANGE = 4
+FLAG_EXHAUSTED = 8
 
 
 class TensorGameError(RuntimeError):
@@ -73,6 +74,9 @@ _SIGNATURES = {
     "tg_pack_actions_i64": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vp]),
     "tg_unpack_actions_i64": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
     "tg_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
+    "tg_demo_gen_philox": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                     _vp, C.c_int64, _vp, _vp, _vp]),
+    "tg_demo_accumulate": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "tg_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64]),
     "tg_host_ctx_destroy": (C.c_int, [_vp]),
     "tg_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),

@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import FLAG_NULL, FLAG_RANGE, FLAG_TERMINAL, TensorGameError, check  # noqa: F401
+from ._lib import FLAG_EXHAUSTED, FLAG_NULL, FLAG_RANGE, FLAG_TERMINAL, TensorGameError, check  # noqa: F401
 
 
 @dataclass(frozen=True)
@@ -133,6 +133,58 @@ def step_batch(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: 
     nnz = torch.empty(B, dtype=torch.int32, device=slab.device) if nnz is None else nnz
     check(_lib.lib().tg_step(_p(slab), _p(tape), _p(out), _p(flags), _p(nnz), B, S, shift, _stream()), "tg_step")
     return out, flags, nnz
+
+
+# ---------------------------------------------------------------- K3
+def _cat_arrays(values, probs):
+    import numpy as np
+
+    v = np.ascontiguousarray(values, dtype=np.int8)
+    p = np.ascontiguousarray(probs, dtype=np.float64)
+    if v.ndim != 1 or v.shape != p.shape or not 1 <= len(v) <= 8:
+        raise TensorGameError("values/probs must be 1-D of equal length <= 8")
+    return v, p
+
+
+def make_synthetic_demos(n_demos: int, max_actions: int, S: int, values=(-1, 0, 1), probs=(0.15, 0.7, 0.15),
+                         shift: int = 1, seed: int = 0, first_demo: int = 0, device="cuda", max_tries: int = 64,
+                         tape: torch.Tensor | None = None, slab: torch.Tensor | None = None):
+    """Throughput-mode demo generation (device Philox stream, tg_demo_gen_philox).
+
+    Returns (tape uint8 (R, N, TP) step-major, slab int8 (N, GP), flags uint8 (N,)).
+    Same distribution and rejection rule as utils.py:203-233; NOT the torch RNG stream --
+    use demos_from_seed for same-seed parity with the reference."""
+    lay = layout(S)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise TensorGameError("make_synthetic_demos needs a CUDA device (there is no CPU path)")
+    v, p = _cat_arrays(values, probs)
+    if tape is None:
+        tape = torch.empty((max_actions, n_demos, lay.token_pitch), dtype=torch.uint8, device=dev)
+    if slab is None:
+        slab = torch.empty((n_demos, lay.game_pitch), dtype=torch.int8, device=dev)
+    flags = torch.empty(n_demos, dtype=torch.uint8, device=dev)
+    stride = tape.stride(0) if max_actions > 1 else n_demos * lay.token_pitch
+    with torch.cuda.device(dev):
+        check(_lib.lib().tg_demo_gen_philox(seed, first_demo, n_demos, max_actions, S, shift, v.ctypes.data, p.ctypes.data,
+                                            len(v), max_tries, _p(tape), stride, _p(slab), _p(flags), _stream()),
+              "tg_demo_gen_philox")
+    return tape, slab, flags
+
+
+def accumulate_demos(tape: torch.Tensor, S: int, shift: int, slab: torch.Tensor | None = None):
+    """slab[n] = sum_r rank1(tape[r, n]) (tg_demo_accumulate).  Returns (slab, flags)."""
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(S)
+    R, N = tape.shape[0], tape.shape[1]
+    if tape.shape[2] != lay.token_pitch:
+        raise TensorGameError(f"tape must be (R, N, {lay.token_pitch})")
+    if slab is None:
+        slab = torch.empty((N, lay.game_pitch), dtype=torch.int8, device=tape.device)
+    flags = torch.empty(N, dtype=torch.uint8, device=tape.device)
+    check(_lib.lib().tg_demo_accumulate(_p(tape), N * lay.token_pitch, N, R, S, shift, _p(slab), _p(flags), _stream()),
+          "tg_demo_accumulate")
+    return slab, flags
 
 
 class HostStepper:

@@ -38,3 +38,18 @@ def tokens_to_tape(tok: np.ndarray) -> np.ndarray:
     tape = np.zeros((B, tp), dtype=np.uint8)
     tape[:, :n] = tok.astype(np.uint8)
     return tape
+
+
+def tokens_to_tape3(tok: np.ndarray) -> np.ndarray:
+    """(N,R,3S) ints -> step-major uint8 (R,N,TP)."""
+    N, R, n = tok.shape
+    _, _, tp = geo(n // 3)
+    tape = np.zeros((R, N, tp), dtype=np.uint8)
+    tape[:, :, :n] = np.transpose(tok, (1, 0, 2)).astype(np.uint8)
+    return tape
+
+
+def tape3_to_tokens(tape: np.ndarray, S: int) -> np.ndarray:
+    """step-major uint8 (R,N,TP) -> int32 (N,R,3S); asserts padding is zero."""
+    assert not tape[:, :, 3 * S :].any(), "tape padding must stay zero"
+    return np.transpose(tape[:, :, : 3 * S], (1, 0, 2)).astype(np.int32)
