@@ -82,6 +82,17 @@ int tg_unpack_actions_i64(const uint8_t *tape, int64_t *actions, int64_t B, int 
 int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz,
             int64_t B, int S, int shift, void *stream);
 
+/* ---- K2: fused K-step rollout --------------------------------------------- */
+/* Applies tape[0..K-1] (step-major uint8 [K][B_total][TP], byte stride
+ * tape_step_stride between steps) to every game, freezing a game once its
+ * head is all zero (the break at act.py:49); steps[b] = actions applied, so
+ * the game's return is -steps[b] (act.py:60-62) before the terminal -get_rank
+ * term.  flags: TG_FLAG_TERMINAL | TG_FLAG_RANGE; nnz of the final head.
+ * Replaces datasets.py:144-153 (_take_actions) and the loop at
+ * training.py:336-342.  In place (slab_out == slab_in) is allowed. */
+int tg_rollout(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out,
+               uint8_t *flags, int32_t *nnz, int32_t *steps, int64_t B, int S, int shift, void *stream);
+
 /* ---- K3: synthetic demonstrations ----------------------------------------- */
 /* Multi-step tapes are step-major: uint8 [R][N_total][TP]; `tape_step_stride`
  * is the byte distance between consecutive steps (N_total*TP), so a rank can
@@ -103,6 +114,22 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
  * list (utils.py:40-53 uvw_to_demo, utils.py:232, datasets.py:141). */
 int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,
                        uint8_t *flags, void *stream);
+
+/* Parity mode: same-seed demos as the reference.  tg_mt19937_fill_f64 is a
+ * HOST function reproducing torch's CPU uniform stream (MT19937, 53-bit
+ * doubles; torch.manual_seed(seed); torch.rand(dtype=float64)), optionally
+ * continuing from a generator state (the 624 words and position stored in
+ * torch.get_rng_state()).  tg_demo_from_ustream consumes a DEVICE copy of
+ * that stream exactly as the reference's rejection loop does (utils.py:
+ * 222-232; Categorical == multinomial, float32 CDF) and emits the first N
+ * demos: result[0] = demos completed (<= N), result[1] = doubles consumed by
+ * them.  workspace: tg_demo_from_ustream_workspace(n_u, S) bytes, 16-aligned. */
+int tg_mt19937_fill_f64(uint32_t seed, int64_t skip, int64_t n, double *out_host);
+int tg_mt19937_fill_f64_state(const uint32_t *state624, int pos, int64_t skip, int64_t n, double *out_host);
+int64_t tg_demo_from_ustream_workspace(int64_t n_u, int S);
+int tg_demo_from_ustream(const double *u, int64_t n_u, const int8_t *values, const float *probs, int n_values, int R, int S,
+                         int shift, int64_t N, uint8_t *tape, int64_t tape_step_stride, int8_t *slab, uint8_t *flags,
+                         int64_t *result, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---- host-buffer path (end-to-end through PCIe) -------------------------- */
 typedef struct tg_host_ctx tg_host_ctx;

@@ -1,0 +1,177 @@
+// tg_rollout.cu -- K2: fused K-step rollout from an action tape (C ABI: tg_rollout).
+//
+// Reference restated: SyntheticDemoDataset._take_actions (datasets.py:144-153)
+// and the greedy loop of training.py:336-342 around _take_action: K successive
+// transitions T <- T - u(x)v(x)w with the game frozen once its head is all
+// zero (the break at act.py:49), one -1 reward per applied action
+// (act.py:60-62).
+//
+// The residual never leaves the SM: thread (game, word column c) keeps its S
+// row words in REGISTERS (offset-binary, see tg_step.cuh) for all K steps, so a
+// step costs one pack(v w) and S IMADs per thread.  Only the tokens stream
+// from HBM (TP bytes per game-step) through a small TMA-fed shared-memory
+// ring.  "Is the game solved" is one shared-memory vote + one CTA barrier per
+// step.  HBM traffic per game: 2*GP + K*TP + 9 bytes.
+#include "tg_step.cuh"
+
+namespace tg {
+
+template <int S, int NT, int NST>
+struct RollCfg {
+    using G = Geo<S>;
+    static constexpr int TG = NT / G::WR;      // games per CTA (one word column per thread)
+    static constexpr int ACTIVE = TG * G::WR;
+    static constexpr int TOK_BYTES = TG * G::TP;
+    static constexpr int SMEM_BYTES = NST * TOK_BYTES + 3 * TG * 4 + 2 * TG * 4 + NST * 8;
+};
+
+template <int S, int NT, int NST>
+__global__ void __launch_bounds__(NT)
+    rollout_kernel(const int8_t *__restrict__ slab_in, const uint8_t *__restrict__ tape, long long tape_step_stride, int K,
+                   int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, int32_t *__restrict__ nnz,
+                   int32_t *__restrict__ steps, long long B, int shift, int chk) {
+    using C = RollCfg<S, NT, NST>;
+    using G = Geo<S>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *s_tok = smem;                                                     // [NST][TG][TP]
+    uint32_t *s_any = reinterpret_cast<uint32_t *>(smem + NST * C::TOK_BYTES); // [3][TG] votes "still non-zero"
+    uint32_t *s_sum = s_any + 3 * C::TG;                                       // [TG] final partial sums
+    uint32_t *s_steps = s_sum + C::TG;                                         // [TG]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_steps + C::TG);           // [NST]
+
+    const int tid = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * C::TG;
+    const int ng = (int)min((long long)C::TG, B - g0);
+    const bool active = tid < C::ACTIVE && (tid / G::WR) < ng;
+    const int g = tid / G::WR;
+    Lane<S> L;
+    L.init(tid < C::ACTIVE ? tid % G::WR : 0);
+
+    for (int i = tid; i < 3 * C::TG; i += NT) s_any[i] = 0;
+    for (int i = tid; i < C::TG; i += NT) s_sum[i] = 0, s_steps[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(&s_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto load_tokens = [&](int t) {
+        const int s = t % NST;
+        mbar_expect_tx(&s_bar[s], (uint32_t)(ng * G::TP));
+        bulk_g2s(s_tok + s * C::TOK_BYTES, tape + (size_t)t * tape_step_stride + g0 * G::TP, (uint32_t)(ng * G::TP), &s_bar[s]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < NST && t < K; t++) load_tokens(t);
+
+    // residual rows of this thread's word column, offset-binary
+    uint32_t row[S];
+    uint32_t nzw = 0, bad = 0;
+    const uint32_t vmask = (L.hv >> 7) * 0xFFu; // bytes that are real entries
+    if (active) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(slab_in + (g0 + g) * G::GP) + L.c;
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            const uint32_t t = src[i * G::WR];
+            nzw |= t & vmask;
+            row[i] = t ^ H4;
+            bad |= ~(row[i] ^ (row[i] << 1)); // the start state must already be inside [-64,63]
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < S; i++) row[i] = H4;
+    }
+    // vote on the initial state (slot 2 is the "step -1" slot)
+    if (active && nzw) s_any[2 * C::TG + g] = 1;
+    __syncthreads();
+    bool alive = active && s_any[2 * C::TG + g] != 0;
+    int until = chk;
+    int my_steps = 0;
+
+    for (int t = 0; t < K; t++) {
+        const int st = t % NST;
+        mbar_wait(&s_bar[st], (uint32_t)(t / NST) & 1u);
+        const int slot = t % 3;
+        if (tid < C::TG) s_any[((t + 1) % 3) * C::TG + tid] = 0; // last read before the previous barrier
+        if (alive) {
+            const uint8_t *tok = s_tok + st * C::TOK_BYTES + g * G::TP;
+            const int32_t vw = pack_vw<S>(tok, L, shift);
+            const uint4 ut = *reinterpret_cast<const uint4 *>(tok);
+            const uint32_t uw[4] = {ut.x, ut.y, ut.z, ut.w};
+            uint32_t any = 0;
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                row[i] += (uint32_t)(shift - (int)((uw[i >> 2] >> (8 * (i & 3))) & 0xFFu)) * (uint32_t)vw;
+                any |= row[i] ^ H4;
+            }
+            if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
+                until = chk;
+#pragma unroll
+                for (int i = 0; i < S; i++) bad |= ~(row[i] ^ (row[i] << 1));
+            }
+            my_steps = t + 1;
+            if (any & vmask) s_any[slot * C::TG + g] = 1;
+        }
+        __syncthreads();
+        if (alive) alive = s_any[slot * C::TG + g] != 0;
+        if (tid == 0 && t + NST < K) load_tokens(t + NST); // stage st was fully read before the barrier
+    }
+
+    // final state out, per-game nnz / flags / steps
+    if (active) {
+        uint32_t cnt = 0;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(slab_out + (g0 + g) * G::GP) + L.c;
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            bad |= ~(row[i] ^ (row[i] << 1));
+            const uint32_t t = row[i] ^ H4;
+            dst[i * G::WR] = t;
+            cnt += ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & L.hv) >> 7;
+        }
+        atomicAdd(&s_sum[g], make_partial(byte_sum(cnt), true, (bad & L.hv) != 0));
+        if (L.c == 0) s_steps[g] = (uint32_t)my_steps;
+    }
+    __syncthreads();
+    for (int q = tid; q < ng; q += NT) {
+        const uint32_t sum = s_sum[q];
+        flags[g0 + q] = (uint8_t)(partial_flags(sum) & ~TG_FLAG_NULL);
+        nnz[g0 + q] = (int32_t)(sum & 0xFFFFu);
+        steps[g0 + q] = (int32_t)s_steps[q];
+    }
+    if constexpr (G::GP > S * G::RP) { // keep the slab tail padding of out-of-place results zero
+        if (slab_out != slab_in)
+            for (int q = tid; q < ng * ((G::GP - S * G::RP) / 4); q += NT) {
+                const int gg = q / ((G::GP - S * G::RP) / 4), w = q % ((G::GP - S * G::RP) / 4);
+                reinterpret_cast<uint32_t *>(slab_out + (g0 + gg) * G::GP + S * G::RP)[w] = 0;
+            }
+    }
+}
+
+template <int S, int NT, int NST>
+static int launch_rollout(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out,
+                          uint8_t *flags, int32_t *nnz, int32_t *steps, long long B, int shift, cudaStream_t st) {
+    using C = RollCfg<S, NT, NST>;
+    const long long grid = (B + C::TG - 1) / C::TG;
+    if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+    const int s3 = shift * shift * shift;
+    const int chk = s3 >= 64 ? 1 : 64 / s3;
+    rollout_kernel<S, NT, NST><<<(int)grid, NT, C::SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B,
+                                                                     shift, chk);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+} // namespace tg
+
+extern "C" int tg_rollout(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out,
+                          uint8_t *flags, int32_t *nnz, int32_t *steps, int64_t B, int S, int shift, void *stream) {
+    if (!tg::supported_S(S) || B < 0 || K < 0 || shift < 1 || shift > 4) return TG_E_ARG;
+    if (B == 0) return TG_OK;
+    if (!slab_in || !slab_out || !flags || !nnz || !steps || (K > 0 && !tape)) return TG_E_ARG;
+    if (((uintptr_t)slab_in | (uintptr_t)slab_out | (uintptr_t)tape | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (S) {
+    case 4: return tg::launch_rollout<4, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, st);
+    case 9: return tg::launch_rollout<9, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, st);
+    case 16: return tg::launch_rollout<16, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, st);
+    }
+    return TG_E_ARG;
+}

@@ -135,6 +135,26 @@ def step_batch(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: 
     return out, flags, nnz
 
 
+# ---------------------------------------------------------------- K2
+def rollout(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: torch.Tensor | None = None):
+    """Apply a step-major tape (K, B, TP) to every game, freezing solved games.
+    Returns (out, flags, nnz, steps).  Reference: datasets.py:144-153, training.py:336-342, act.py:49."""
+    _need_cuda(slab, "slab", torch.int8)
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(S)
+    B = slab.shape[0]
+    if tape.dim() != 3 or tape.shape[1] != B or tape.shape[2] != lay.token_pitch or slab.shape[1] != lay.game_pitch:
+        raise TensorGameError(f"expected slab (B,{lay.game_pitch}) and tape (K,B,{lay.token_pitch})")
+    K = tape.shape[0]
+    out = torch.empty_like(slab) if out is None else out
+    flags = torch.empty(B, dtype=torch.uint8, device=slab.device)
+    nnz = torch.empty(B, dtype=torch.int32, device=slab.device)
+    steps = torch.empty(B, dtype=torch.int32, device=slab.device)
+    check(_lib.lib().tg_rollout(_p(slab), _p(tape), B * lay.token_pitch, K, _p(out), _p(flags), _p(nnz), _p(steps), B, S, shift,
+                                _stream()), "tg_rollout")
+    return out, flags, nnz, steps
+
+
 # ---------------------------------------------------------------- K3
 def _cat_arrays(values, probs):
     import numpy as np
@@ -185,6 +205,78 @@ def accumulate_demos(tape: torch.Tensor, S: int, shift: int, slab: torch.Tensor 
     check(_lib.lib().tg_demo_accumulate(_p(tape), N * lay.token_pitch, N, R, S, shift, _p(slab), _p(flags), _stream()),
           "tg_demo_accumulate")
     return slab, flags
+
+
+def torch_cpu_stream(n: int, seed: int | None = None, generator: torch.Generator | None = None, skip: int = 0):
+    """The next n doubles torch's CPU generator would produce (torch.rand(dtype=float64)), computed by the
+    library's MT19937 (tg_mt19937_fill_f64*) WITHOUT advancing torch's generator.  seed=None continues from
+    `generator` (default: the global CPU generator)."""
+    import numpy as np
+
+    out = np.empty(n, dtype=np.float64)
+    if seed is not None:
+        check(_lib.lib().tg_mt19937_fill_f64(seed & 0xFFFFFFFF, skip, n, out.ctypes.data), "tg_mt19937_fill_f64")
+        return out
+    st = (generator.get_state() if generator is not None else torch.get_rng_state()).numpy().tobytes()
+    # at::mt19937 state blob: seed u64 | left i32 | seeded i32 | next u64 | state[624] u64 ...; `left` numbers remain
+    # before the next twist, so the read position is 624 - left + 1 (a freshly seeded generator has left == 1)
+    pos = 624 - int.from_bytes(st[8:12], "little", signed=True) + 1
+    words = np.frombuffer(st, dtype=np.uint64, count=624, offset=24).astype(np.uint32)
+    check(_lib.lib().tg_mt19937_fill_f64_state(words.ctypes.data, pos, skip, n, out.ctypes.data), "tg_mt19937_fill_f64_state")
+    return out
+
+
+def demos_from_ustream(ustream, n_demos: int, max_actions: int, S: int, values, probs, shift: int, device="cuda"):
+    """Parity-mode demos from an explicit uniform stream (numpy float64, host).  Returns
+    (tape (R,N,TP), slab (N,GP), flags (N,), demos_done, doubles_consumed)."""
+    import numpy as np
+
+    lay = layout(S)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise TensorGameError("demos_from_ustream needs a CUDA device (there is no CPU path)")
+    v = np.ascontiguousarray(values, dtype=np.int8)
+    p = np.ascontiguousarray(probs, dtype=np.float32)
+    u = torch.from_numpy(np.ascontiguousarray(ustream, dtype=np.float64)).to(dev)
+    n_u = u.numel()
+    tape = torch.zeros((max_actions, n_demos, lay.token_pitch), dtype=torch.uint8, device=dev)
+    slab = torch.empty((n_demos, lay.game_pitch), dtype=torch.int8, device=dev)
+    flags = torch.empty(n_demos, dtype=torch.uint8, device=dev)
+    result = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws_bytes = int(_lib.lib().tg_demo_from_ustream_workspace(n_u, S))
+    ws = torch.empty(ws_bytes + 16, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().tg_demo_from_ustream(_p(u), n_u, v.ctypes.data, p.ctypes.data, len(v), max_actions, S, shift, n_demos,
+                                              _p(tape), n_demos * lay.token_pitch, _p(slab), _p(flags), _p(result), _p(ws),
+                                              ws_bytes, _stream()), "tg_demo_from_ustream")
+    done, consumed = (int(x) for x in result.tolist())
+    return tape, slab, flags, done, consumed
+
+
+def demos_from_seed(n_demos: int, max_actions: int, S: int, values=(-1, 0, 1), probs=(0.15, 0.7, 0.15), shift: int = 1,
+                    seed: int | None = None, generator: torch.Generator | None = None, device="cuda", advance: bool = True):
+    """Same demos as the reference's loop (utils.py:203-233 / datasets.py:124-142) run from torch's CPU
+    generator: seed=None continues from the global (or given) generator and, if advance, leaves it where
+    the reference would have left it.  Returns (tape, slab, flags, doubles_consumed)."""
+    import numpy as np
+
+    pv = np.asarray(probs, dtype=np.float64)
+    p0 = float(pv[np.asarray(values) == 0].sum() / pv.sum())
+    accept = max((1.0 - p0 ** S) ** 3, 1e-3)
+    n_u = int(n_demos * max_actions * 3 * S / accept * 1.25) + 64 * 3 * S
+    while True:
+        u = torch_cpu_stream(n_u, seed=seed, generator=generator)
+        tape, slab, flags, done, consumed = demos_from_ustream(u, n_demos, max_actions, S, values, probs, shift, device)
+        if done == n_demos:
+            break
+        n_u *= 2
+    if seed is None and advance:  # move torch's generator to where the reference loop would have left it
+        left = consumed
+        while left > 0:
+            k = min(left, 1 << 22)
+            torch.rand(k, dtype=torch.float64, generator=generator)
+            left -= k
+    return tape, slab, flags, consumed
 
 
 class HostStepper:

@@ -44,3 +44,22 @@ def test_no_cpu_fallback():
     tape = torch.zeros((2, 32), dtype=torch.uint8)
     with pytest.raises(env.TensorGameError):
         env.step_batch(slab, tape, 9, 2)
+
+
+def test_host_mt19937_stream_matches_torch():
+    # host-side logic of parity-mode demo generation: the library's MT19937 continues torch's CPU generator
+    import numpy as np
+    import torch
+
+    from mat_mul_b200 import env
+
+    torch.manual_seed(5)
+    a = env.torch_cpu_stream(10)
+    assert np.array_equal(a, torch.rand(10, dtype=torch.float64).numpy())
+    c = env.torch_cpu_stream(700)  # crosses a twist, starts mid-state
+    assert np.array_equal(c, torch.rand(700, dtype=torch.float64).numpy())
+    assert np.array_equal(env.torch_cpu_stream(5, seed=5), a[:5])
+    assert np.array_equal(env.torch_cpu_stream(5, seed=5, skip=3), a[3:8])
+    g = torch.Generator().manual_seed(77)
+    x = env.torch_cpu_stream(1300, generator=g)
+    assert np.array_equal(x, torch.rand(1300, dtype=torch.float64, generator=g).numpy())
