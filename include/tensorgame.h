@@ -52,6 +52,7 @@ extern "C" {
 #define TG_FLAG_NULL 2u     /* rank-1 update all zero: utils.py:191-194 */
 #define TG_FLAG_RANGE 4u    /* a residual entry left [-64, 63]: int8 slab no longer guaranteed */
 #define TG_FLAG_EXHAUSTED 8u /* demo generation: a term hit max_tries and was forced to a unit triple */
+#define TG_FLAG_TOKEN_RANGE 16u /* change of basis: a transformed factor entry left [-shift_out, shift_out] */
 
 int tg_version(void);
 int tg_last_cuda_error(void);
@@ -130,6 +131,49 @@ int64_t tg_demo_from_ustream_workspace(int64_t n_u, int S);
 int tg_demo_from_ustream(const double *u, int64_t n_u, const int8_t *values, const float *probs, int n_values, int R, int S,
                          int shift, int64_t N, uint8_t *tape, int64_t tape_step_stride, int8_t *slab, uint8_t *flags,
                          int64_t *result, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- K4: training-sample batcher ------------------------------------------ */
+/* SyntheticDemoDataset.__getitem__ (datasets.py:77-122) for nb sample indices
+ * idx[b] = demo * R + action, read from the in-HBM demo store (step-major tape
+ * + target slab): states float32 [nb][dim_t][S][S][S], scalars [nb] = R - a,
+ * actions int64 [nb][3S], rewards [nb] = -(a+1).  replay_shift is the shift
+ * action_to_tensor applies while replaying (the reference hard-codes 1,
+ * utils.py:88-96); pass the demos' own shift for the true residual. */
+int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *slab, int64_t N, int R, int S, int dim_t,
+                   int replay_shift, const int64_t *idx, int64_t nb, float *states, float *scalars, int64_t *actions,
+                   float *rewards, void *stream);
+
+/* ---- K6: rank reward ------------------------------------------------------ */
+/* ranks[b] = sum_i rank(T_b[i,:,:]) -- get_rank (utils.py:134-140), the
+ * terminal reward -get_rank of act.py:59,214.  Exact rank over GF(2^31-1)
+ * instead of the reference's float32 SVD. */
+int tg_slice_rank(const int8_t *slab, int32_t *ranks, int64_t B, int S, void *stream);
+
+/* ---- K7: state keys ------------------------------------------------------- */
+/* 64-bit key per head tensor, replacing the string keys of utils.py:164-169
+ * used by the MCTS tree (act.py:37,93,146,171,189,192,210): equal states <=>
+ * equal keys (up to a 2^-64 collision); the all-zero state has key 0. */
+int tg_state_key(const int8_t *slab, uint64_t *keys, int64_t B, int S, void *stream);
+
+/* ---- K5: change-of-basis augmentation ------------------------------------- */
+/* ABSENT from the reference; specified from the AlphaTensor paper (Methods,
+ * "Change of basis"): T'[i][j][k] = sum_abc A[i][a] B[j][b] C[k][c] T[a][b][c].
+ * mats: int8 [N or 1][3][S][S] = (A, B, C) row-major, one triple per game
+ * (per_game != 0) or one shared triple.  slab_out must differ from slab_in.
+ * flags (may be NULL): TG_FLAG_RANGE if an entry of T' left [-64,63] (the
+ * int8 slab's guaranteed zone; intermediates are int32 and exact). */
+int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, int8_t *slab_out, uint8_t *flags, int64_t N,
+                       int S, void *stream);
+/* factors follow: u' = A u, v' = B v, w' = C w for every step of a step-major
+ * tape; token' = coef' + shift_out.  ORs TG_FLAG_TOKEN_RANGE into flags[n] if a
+ * transformed entry leaves [-shift_out, shift_out] (flags must be initialised). */
+int tg_change_of_basis_factors(const uint8_t *tape_in, int64_t in_step_stride, int shift_in, const int8_t *mats, int per_game,
+                               uint8_t *tape_out, int64_t out_step_stride, int shift_out, uint8_t *flags, int64_t N, int R,
+                               int S, void *stream);
+/* random unimodular triples M = L*U (L unit lower, U upper with +-1 diagonal,
+ * off-diagonal entries -1/0/+1, P(non-zero) = p_nonzero quantised to 1/128),
+ * Philox-keyed by (seed, first + n) like the demo stream -> int8 [N][3][S][S]. */
+int tg_sample_unimodular(uint64_t seed, uint64_t first, int64_t N, int S, double p_nonzero, int8_t *mats, void *stream);
 
 /* ---- host-buffer path (end-to-end through PCIe) -------------------------- */
 typedef struct tg_host_ctx tg_host_ctx;

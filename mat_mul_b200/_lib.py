@@ -25,6 +25,7 @@ FLAG_TERMINAL = 1
 FLAG_NULL = 2
 FLAG_RANGE = 4
 FLAG_EXHAUSTED = 8
+FLAG_TOKEN_RANGE = 16
 
 
 class TensorGameError(RuntimeError):
@@ -78,6 +79,14 @@ _SIGNATURES = {
     "tg_demo_gen_philox": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
                                      _vp, C.c_int64, _vp, _vp, _vp]),
     "tg_demo_accumulate": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "tg_demo_sample": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp,
+                                 _vp, _vp]),
+    "tg_slice_rank": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "tg_state_key": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "tg_change_of_basis": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp]),
+    "tg_change_of_basis_factors": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int64,
+                                             C.c_int, C.c_int, _vp]),
+    "tg_sample_unimodular": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_double, _vp, _vp]),
     "tg_mt19937_fill_f64": (C.c_int, [C.c_uint32, C.c_int64, C.c_int64, _vp]),
     "tg_mt19937_fill_f64_state": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, _vp]),
     "tg_demo_from_ustream_workspace": (C.c_int64, [C.c_int64, C.c_int]),

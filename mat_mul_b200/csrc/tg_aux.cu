@@ -1,0 +1,254 @@
+// tg_aux.cu -- K4 demo_sample (training-sample batcher), K6 slice_rank, K7 state_key.
+#include "tg_step.cuh"
+
+namespace tg {
+
+// ------------------------------------------------------------------ K4
+// SyntheticDemoDataset.__getitem__ (datasets.py:77-122) for a batch of sample
+// indices, straight from the in-HBM demo store (no torch.load, no Python
+// replay).  idx = demo * R + action.  Emits, per sample,
+//   state  float32 [dim_t][S][S][S]: slot 0 = target - sum_{j>a} rank1(tok_j),
+//          slots 1.. = rank1 of actions min(a+dim_t-1,R-1) .. a+1, zero padded
+//   scalar float32 = R - a, reward float32 = -(a+1), action int64 [3S] = tok_a.
+// rank1 uses coefficient = token - replay_shift; the reference hard-codes 1
+// there, callers wanting the true residual pass the demo's shift.
+// One thread per (sample, word column); per-entry int32 accumulators, so any
+// magnitude the float32 reference can hold exactly is exact here too.
+template <int S>
+__device__ __forceinline__ void vw_bytes(const uint8_t *tok, const Lane<S> &L, int shift, int vw[4]) {
+    const int vA = (int)tok[L.off_vA] - shift, vB = (int)tok[L.off_vB] - shift;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const bool inA = (L.maskA >> (8 * b)) & 1u, inB = (L.maskB >> (8 * b)) & 1u;
+        const int w = (int)tok[L.off_w[b]] - shift;
+        vw[b] = inA ? vA * w : (inB ? vB * w : 0);
+    }
+}
+
+template <int S>
+__global__ void demo_sample_kernel(const uint8_t *__restrict__ tape, long long tape_step_stride,
+                                   const int8_t *__restrict__ slab, long long N, int R, int dim_t, int replay_shift,
+                                   const long long *__restrict__ idx, long long nb, float *__restrict__ states,
+                                   float *__restrict__ scalars, long long *__restrict__ actions,
+                                   float *__restrict__ rewards) {
+    using G = Geo<S>;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long b = t / G::WR;
+    if (b >= nb) return;
+    Lane<S> L;
+    L.init((int)(t % G::WR));
+    const long long id = idx[b];
+    const long long demo = id / R;
+    const int a = (int)(id - demo * R);
+    if (demo < 0 || demo >= N) return;
+    const uint8_t *tk = tape + demo * G::TP;
+    // head
+    int acc[S][4];
+    const int8_t *tg = slab + demo * G::GP + 4 * L.c;
+#pragma unroll
+    for (int i = 0; i < S; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[i][q] = (int)tg[i * G::RP + q];
+    for (int j = a + 1; j < R; j++) {
+        const uint8_t *tok = tk + (size_t)j * tape_step_stride;
+        int vw[4];
+        vw_bytes<S>(tok, L, replay_shift, vw);
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            const int u = (int)tok[i] - replay_shift;
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[i][q] -= u * vw[q];
+        }
+    }
+    float *st = states + b * (long long)dim_t * G::S3;
+#pragma unroll
+    for (int i = 0; i < S; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (4 * L.c + q < G::S2) st[i * G::S2 + 4 * L.c + q] = (float)acc[i][q];
+    // history slots: rank-1 tensors of the next actions, latest first
+    const int hi = min(a + dim_t, R);
+    for (int s = 1; s < dim_t; s++) {
+        const int j = hi - s;
+        float *ss = st + (long long)s * G::S3;
+        if (j >= a + 1) {
+            const uint8_t *tok = tk + (size_t)j * tape_step_stride;
+            int vw[4];
+            vw_bytes<S>(tok, L, replay_shift, vw);
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const int u = (int)tok[i] - replay_shift;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (4 * L.c + q < G::S2) ss[i * G::S2 + 4 * L.c + q] = (float)(u * vw[q]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < S; i++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (4 * L.c + q < G::S2) ss[i * G::S2 + 4 * L.c + q] = 0.f;
+        }
+    }
+    if (L.c == 0) {
+        scalars[b] = (float)(R - a);
+        rewards[b] = -(float)(a + 1);
+    }
+    const uint8_t *ta = tk + (size_t)a * tape_step_stride;
+    for (int q = L.c; q < 3 * S; q += G::WR) actions[b * 3 * S + q] = (long long)ta[q];
+}
+
+// ------------------------------------------------------------------ K6
+// get_rank (utils.py:134-140): sum over the S slices T[i,:,:] of the matrix
+// rank.  The reference takes a float32 SVD; here the rank is computed exactly
+// over GF(p), p = 2^31-1, by fraction-free elimination (row <- row*piv -
+// row[c]*pivrow), one matrix per group of S lanes, lane = matrix row.  rank_p
+// <= rank_Q with equality unless p divides a pivot minor (probability ~S/p per
+// matrix); the small integer matrices of the game are far from that.
+__device__ __forceinline__ uint32_t mulmod31(uint32_t a, uint32_t b) {
+    const unsigned long long z = (unsigned long long)a * b;
+    uint32_t r = (uint32_t)(z & 0x7FFFFFFFu) + (uint32_t)(z >> 31);
+    r = (r & 0x7FFFFFFFu) + (r >> 31);
+    return r >= 0x7FFFFFFFu ? r - 0x7FFFFFFFu : r;
+}
+
+template <int S>
+__global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__restrict__ ranks, long long B) {
+    using G = Geo<S>;
+    constexpr int LG = S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32)); // lanes per matrix (power of two)
+    constexpr int MPW = 32 / LG;                                        // matrices per warp
+    constexpr uint32_t P = 0x7FFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LG, r = lane % LG;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long mat = warp * MPW + sub; // matrix index = game * S + slice
+    const long long game = mat / S;
+    const int slice = (int)(mat - game * S);
+    const bool live = game < B && r < S;
+    uint32_t row[S];
+#pragma unroll
+    for (int c = 0; c < S; c++) {
+        int v = 0;
+        if (live) v = slab[game * G::GP + slice * G::RP + r * S + c];
+        row[c] = v >= 0 ? (uint32_t)v : P - (uint32_t)(-v);
+    }
+    const uint32_t gmask = (LG == 32) ? 0xFFFFFFFFu : (((1u << LG) - 1u) << (sub * LG));
+    bool used = !live;
+    int rank = 0;
+#pragma unroll
+    for (int c = 0; c < S; c++) {
+        const uint32_t cand = __ballot_sync(0xFFFFFFFFu, !used && row[c] != 0) & gmask;
+        const bool has = cand != 0; // uniform within the group; all 32 lanes keep executing the same shuffles
+        const int pl = has ? __ffs(cand) - 1 : lane;
+        const uint32_t pv = __shfl_sync(0xFFFFFFFFu, row[c], pl);
+        const uint32_t mine = row[c];
+        const bool elim = has && !used && lane != pl && mine != 0;
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            const uint32_t pk = __shfl_sync(0xFFFFFFFFu, row[k], pl);
+            if (elim) {
+                const uint32_t x = mulmod31(row[k], pv), y = mulmod31(mine, pk);
+                row[k] = x >= y ? x - y : x + P - y;
+            }
+        }
+        if (has && lane == pl) used = true;
+        rank += has ? 1 : 0;
+    }
+    // every lane of a group counted the same pivots; add the slices of a game
+    if (live && r == 0) atomicAdd(&ranks[game], rank);
+}
+
+// ------------------------------------------------------------------ K7
+// 64-bit state key replacing the string key of utils.py:164-169 (dict key of
+// the MCTS tree, act.py:37...210): sum over non-zero entries e of
+// splitmix64((e+1) << 32 | uint32(value)), e the dense index (i*S+j)*S+k.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <int S>
+__global__ void state_key_kernel(const int8_t *__restrict__ slab, unsigned long long *__restrict__ keys, long long B) {
+    using G = Geo<S>;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long g = t / G::WR;
+    if (g >= B) return;
+    const int c = (int)(t % G::WR);
+    unsigned long long h = 0;
+    const uint32_t *col = reinterpret_cast<const uint32_t *>(slab + g * G::GP) + c;
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        const uint32_t w = col[i * G::WR];
+        if (w == 0) continue;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int v = (int)(int8_t)((w >> (8 * q)) & 0xFFu);
+            const int jk = 4 * c + q;
+            if (v != 0 && jk < G::S2)
+                h += splitmix64(((unsigned long long)(uint32_t)(i * G::S2 + jk + 1) << 32) | (uint32_t)v);
+        }
+    }
+    if (h) atomicAdd(&keys[g], h);
+}
+
+} // namespace tg
+
+#define TG_SWITCH_S(S, ...) \
+    switch (S) {            \
+    case 4: { constexpr int kS = 4; __VA_ARGS__; } break;   \
+    case 9: { constexpr int kS = 9; __VA_ARGS__; } break;   \
+    case 16: { constexpr int kS = 16; __VA_ARGS__; } break; \
+    default: return TG_E_ARG; \
+    }
+
+extern "C" {
+
+int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *slab, int64_t N, int R, int S, int dim_t,
+                   int replay_shift, const int64_t *idx, int64_t nb, float *states, float *scalars, int64_t *actions,
+                   float *rewards, void *stream) {
+    if (!tg::supported_S(S) || N < 0 || R < 1 || dim_t < 1 || nb < 0) return TG_E_ARG;
+    if (nb == 0) return TG_OK;
+    if (!tape || !slab || !idx || !states || !scalars || !actions || !rewards) return TG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TG_SWITCH_S(S, {
+        const long long threads = nb * tg::Geo<kS>::WR;
+        tg::demo_sample_kernel<kS><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+            tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb, states, scalars,
+            (long long *)actions, rewards);
+    });
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_slice_rank(const int8_t *slab, int32_t *ranks, int64_t B, int S, void *stream) {
+    if (!tg::supported_S(S) || B < 0) return TG_E_ARG;
+    if (B == 0) return TG_OK;
+    if (!slab || !ranks) return TG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TG_CUDA(cudaMemsetAsync(ranks, 0, (size_t)B * 4, st));
+    TG_SWITCH_S(S, {
+        constexpr int LG = kS <= 4 ? 4 : (kS <= 8 ? 8 : (kS <= 16 ? 16 : 32));
+        const long long warps = (B * kS + (32 / LG) - 1) / (32 / LG);
+        tg::slice_rank_kernel<kS><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(slab, ranks, B);
+    });
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_state_key(const int8_t *slab, uint64_t *keys, int64_t B, int S, void *stream) {
+    if (!tg::supported_S(S) || B < 0) return TG_E_ARG;
+    if (B == 0) return TG_OK;
+    if (!slab || !keys) return TG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TG_CUDA(cudaMemsetAsync(keys, 0, (size_t)B * 8, st));
+    TG_SWITCH_S(S, {
+        const long long threads = B * tg::Geo<kS>::WR;
+        tg::state_key_kernel<kS><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(slab, (unsigned long long *)keys, B);
+    });
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+} // extern "C"

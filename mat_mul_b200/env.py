@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import FLAG_EXHAUSTED, FLAG_NULL, FLAG_RANGE, FLAG_TERMINAL, TensorGameError, check  # noqa: F401
+from ._lib import FLAG_EXHAUSTED, FLAG_NULL, FLAG_RANGE, FLAG_TERMINAL, FLAG_TOKEN_RANGE, TensorGameError, check  # noqa: F401
 
 
 @dataclass(frozen=True)
@@ -277,6 +277,83 @@ def demos_from_seed(n_demos: int, max_actions: int, S: int, values=(-1, 0, 1), p
             torch.rand(k, dtype=torch.float64, generator=generator)
             left -= k
     return tape, slab, flags, consumed
+
+
+# ---------------------------------------------------------------- K4 / K6 / K7
+def demo_samples(tape: torch.Tensor, slab: torch.Tensor, idx: torch.Tensor, S: int, dim_t: int, replay_shift: int = 1):
+    """Batch of SyntheticDemoDataset.__getitem__ results (datasets.py:77-122) from the in-HBM demo store.
+    Returns (states f32 (nb,dim_t,S,S,S), scalars f32 (nb,1), actions i64 (nb,3S), rewards f32 (nb,1))."""
+    _need_cuda(tape, "tape", torch.uint8)
+    _need_cuda(slab, "slab", torch.int8)
+    _need_cuda(idx, "idx", torch.int64)
+    lay = layout(S)
+    R, N = tape.shape[0], tape.shape[1]
+    nb = idx.numel()
+    dev = tape.device
+    states = torch.empty((nb, dim_t, S, S, S), dtype=torch.float32, device=dev)
+    scalars = torch.empty((nb, 1), dtype=torch.float32, device=dev)
+    actions = torch.empty((nb, 3 * S), dtype=torch.int64, device=dev)
+    rewards = torch.empty((nb, 1), dtype=torch.float32, device=dev)
+    check(_lib.lib().tg_demo_sample(_p(tape), N * lay.token_pitch, _p(slab), N, R, S, dim_t, replay_shift, _p(idx), nb,
+                                    _p(states), _p(scalars), _p(actions), _p(rewards), _stream()), "tg_demo_sample")
+    return states, scalars, actions, rewards
+
+
+def slice_rank(slab: torch.Tensor, S: int) -> torch.Tensor:
+    """get_rank per game (utils.py:134-140): int32 (B,)."""
+    _need_cuda(slab, "slab", torch.int8)
+    ranks = torch.empty(slab.shape[0], dtype=torch.int32, device=slab.device)
+    check(_lib.lib().tg_slice_rank(_p(slab), _p(ranks), slab.shape[0], S, _stream()), "tg_slice_rank")
+    return ranks
+
+
+def state_keys(slab: torch.Tensor, S: int) -> torch.Tensor:
+    """64-bit state keys (as int64 bit patterns), replacing utils.state_to_str dict keys."""
+    _need_cuda(slab, "slab", torch.int8)
+    keys = torch.empty(slab.shape[0], dtype=torch.int64, device=slab.device)
+    check(_lib.lib().tg_state_key(_p(slab), _p(keys), slab.shape[0], S, _stream()), "tg_state_key")
+    return keys
+
+
+# ---------------------------------------------------------------- K5
+def sample_unimodular(n: int, S: int, seed: int = 0, first: int = 0, p_nonzero: float = 0.3, device="cuda") -> torch.Tensor:
+    """Random unimodular (A, B, C) per game: int8 (n, 3, S, S) (tg_sample_unimodular)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise TensorGameError("sample_unimodular needs a CUDA device (there is no CPU path)")
+    mats = torch.empty((n, 3, S, S), dtype=torch.int8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().tg_sample_unimodular(seed, first, n, S, float(p_nonzero), _p(mats), _stream()), "tg_sample_unimodular")
+    return mats
+
+
+def change_of_basis(slab: torch.Tensor, mats: torch.Tensor, S: int, tape: torch.Tensor | None = None, shift: int = 0,
+                    shift_out: int | None = None):
+    """T' = T x1 A x2 B x3 C (and u' = A u, v' = B v, w' = C w for a step-major tape).
+
+    mats int8 (N, 3, S, S) per game or (1, 3, S, S) / (3, S, S) shared.  Returns (slab', flags) or
+    (slab', tape', flags).  Not in the reference: AlphaTensor paper, Methods "Change of basis"."""
+    _need_cuda(slab, "slab", torch.int8)
+    _need_cuda(mats, "mats", torch.int8)
+    N = slab.shape[0]
+    m = mats.reshape(-1, 3, S, S)
+    if m.shape[0] not in (1, N):
+        raise TensorGameError("mats must hold one (A,B,C) triple or one per game")
+    per_game = int(m.shape[0] == N and N > 1)
+    out = torch.empty_like(slab)
+    flags = torch.zeros(N, dtype=torch.uint8, device=slab.device)
+    check(_lib.lib().tg_change_of_basis(_p(slab), _p(m), per_game, _p(out), _p(flags), N, S, _stream()), "tg_change_of_basis")
+    if tape is None:
+        return out, flags
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(S)
+    R = tape.shape[0]
+    shift_out = shift if shift_out is None else shift_out
+    tape_out = torch.empty_like(tape)
+    check(_lib.lib().tg_change_of_basis_factors(_p(tape), N * lay.token_pitch, shift, _p(m), per_game, _p(tape_out),
+                                                N * lay.token_pitch, shift_out, _p(flags), N, R, S, _stream()),
+          "tg_change_of_basis_factors")
+    return out, tape_out, flags
 
 
 class HostStepper:

@@ -664,6 +664,38 @@ void orc_demos_philox_batch(uint64_t seed, uint64_t d0, int64_t n, const int32_t
     if (exhausted) *exhausted = ex;
 }
 
+/* Random unimodular triple (ours): M_f = L*U for f = 0,1,2 (A,B,C).  Entry
+ * (r,c) of the draw grid uses byte (r*S+c)%16 (little-endian within the four
+ * words) of Philox block (r*S+c)/16 with ctr = (block, f, 0x6D617473, d_lo)
+ * and the demo-stream key; low 7 bits < thr_nz => magnitude 1, top bit => sign.
+ * L takes the draws below the diagonal (unit diagonal), U those above it and
+ * the sign of the diagonal draw as its +-1 diagonal.  mats [3][S][S]. */
+void orc_sample_unimodular(uint64_t seed, uint64_t d, int S, uint32_t thr_nz, int32_t *mats) {
+    uint32_t key[2] = {(uint32_t)seed ^ ((uint32_t)(d >> 32) * 0x9E3779B9u), (uint32_t)(seed >> 32)};
+    for (int f = 0; f < 3; f++) {
+        int32_t L[256], U[256];
+        uint32_t blk[4] = {0, 0, 0, 0};
+        for (int e = 0; e < S * S; e++) {
+            if ((e & 15) == 0) {
+                uint32_t ctr[4] = {(uint32_t)(e >> 4), (uint32_t)f, 0x6D617473u, (uint32_t)d};
+                orc_philox4x32_10(ctr, key, blk);
+            }
+            uint32_t byte = (blk[(e >> 2) & 3] >> (8 * (e & 3))) & 0xFFu;
+            int r = e / S, c = e % S;
+            int mag = (byte & 0x7Fu) < thr_nz ? 1 : 0;
+            int val = (byte & 0x80u) ? -mag : mag;
+            L[e] = r > c ? val : (r == c ? 1 : 0);
+            U[e] = r < c ? val : (r == c ? ((byte & 0x80u) ? -1 : 1) : 0);
+        }
+        for (int r = 0; r < S; r++)
+            for (int c = 0; c < S; c++) {
+                int32_t acc = 0;
+                for (int k = 0; k < S; k++) acc += L[r * S + k] * U[k * S + c];
+                mats[(f * S + r) * S + c] = acc;
+            }
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* state key (ours; replaces the string key of utils.py:164-169)       */
 /* ------------------------------------------------------------------ */

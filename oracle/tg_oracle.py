@@ -256,6 +256,15 @@ def change_of_basis_factors(factors, A, Bm, Cm) -> np.ndarray:
     return out
 
 
+def sample_unimodular(seed: int, first: int, n: int, S: int, p_nonzero: float = 0.3) -> np.ndarray:
+    """Our unimodular sampler contract -> int32 (n, 3, S, S)."""
+    mats = np.empty((n, 3, S, S), dtype=np.int32)
+    thr = int(p_nonzero * 128.0)
+    for i in range(n):
+        lib().orc_sample_unimodular(C.c_uint64(seed), C.c_uint64(first + i), C.c_int(S), C.c_uint32(thr), _p(mats[i]))
+    return mats
+
+
 def state_key_batch(T) -> np.ndarray:
     T = _i32(T)
     B, S = T.shape[0], T.shape[-1]

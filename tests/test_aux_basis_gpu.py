@@ -1,0 +1,135 @@
+"""GPU parity of K4 demo_sample, K5 change of basis, K6 slice rank, K7 state key."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tg_oracle as orc
+from tests.helpers import dense_to_slab, slab_to_dense, tape3_to_tokens, tokens_to_tape3
+
+pytestmark = pytest.mark.gpu
+
+V5, P5 = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05)
+
+
+@pytest.fixture(scope="module")
+def env():
+    from mat_mul_b200 import env as e
+
+    assert torch.cuda.is_available()
+    return e
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_demo_sample_matches_reference_getitem(env, golden, tag):
+    # datasets.py:77-122 for EVERY index of three reference demos, incl. the shift-1 replay quirk (tag c)
+    g = golden["getitem"]
+    R, dim_t, S, shift, n_demos = (int(x) for x in g[f"{tag}_cfg"])
+    tape = torch.from_numpy(tokens_to_tape3(g[f"{tag}_tokens"])).cuda()
+    slab = torch.from_numpy(dense_to_slab(g[f"{tag}_targets"])).cuda()
+    idx = torch.arange(n_demos * R, device="cuda")
+    idx = idx[torch.randperm(len(idx), device="cuda")]
+    states, scalars, actions, rewards = env.demo_samples(tape, slab, idx, S, dim_t, replay_shift=1)
+    order = idx.cpu().numpy()
+    assert np.array_equal(states.cpu().numpy(), g[f"{tag}_states"][order].astype(np.float32))
+    assert np.array_equal(scalars.cpu().numpy(), g[f"{tag}_scalars"][order])
+    assert np.array_equal(actions.cpu().numpy(), g[f"{tag}_actions"][order])
+    assert np.array_equal(rewards.cpu().numpy(), g[f"{tag}_rewards"][order])
+    assert states.dtype == torch.float32 and actions.dtype == torch.int64 and scalars.shape == (len(order), 1)
+
+
+@pytest.mark.parametrize("S,R,dim_t", [(4, 7, 3), (9, 23, 2), (16, 12, 4)])
+def test_demo_sample_random_vs_oracle(env, S, R, dim_t):
+    N, shift = 40, 2
+    tok, tgt, _ = orc.demos_seeded(4, V5, P5, R, S, shift, N)
+    tape = torch.from_numpy(tokens_to_tape3(tok)).cuda()
+    slab = torch.from_numpy(dense_to_slab(tgt)).cuda()
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, N * R, 300)
+    for rs in (1, 2):
+        st, sc, ac, rw = env.demo_samples(tape, slab, torch.from_numpy(idx).cuda(), S, dim_t, replay_shift=rs)
+        for b in (0, 7, 150, 299):
+            d, a = divmod(int(idx[b]), R)
+            ws, wsc, wa, wr = orc.demo_getitem(tok[d], tgt[d], dim_t, a, replay_shift=rs)
+            assert np.array_equal(st[b].cpu().numpy(), ws.astype(np.float32))
+            assert sc[b].item() == wsc and rw[b].item() == wr and np.array_equal(ac[b].cpu().numpy(), wa)
+    # with the demos' own shift the head is the true residual: all actions up to a, i.e. zero before action 0 is undone
+    st, _, _, _ = env.demo_samples(tape, slab, torch.arange(0, N * R, R, device="cuda"), S, 1, replay_shift=shift)
+    first = np.stack([orc.action_to_tensor(tok[d, 0], shift) for d in range(N)])
+    assert np.array_equal(st[:, 0].cpu().numpy(), first.astype(np.float32))
+
+
+@pytest.mark.parametrize("S", [4, 9, 16])
+def test_slice_rank_matches_reference_get_rank(env, golden, S):
+    g = golden["ranks"]
+    slab = torch.from_numpy(dense_to_slab(g[f"S{S}_T"])).cuda()
+    assert np.array_equal(env.slice_rank(slab, S).cpu().numpy(), g[f"S{S}_rank"])
+
+
+def test_slice_rank_matmul_and_large(env, golden):
+    for n, want in zip((2, 3, 4), golden["ranks"]["mm_rank"]):
+        slab = torch.from_numpy(dense_to_slab(orc.build_matmul_tensor(n)[None])).cuda()
+        assert env.slice_rank(slab, n * n).item() == want
+    rng = np.random.default_rng(3)
+    T = rng.integers(-60, 60, (3000, 9, 9, 9)) * (rng.random((3000, 9, 9, 9)) < 0.25)
+    T[::7] = 0
+    got = env.slice_rank(torch.from_numpy(dense_to_slab(T)).cuda(), 9).cpu().numpy()
+    assert np.array_equal(got, orc.slice_rank_batch(T))
+
+
+@pytest.mark.parametrize("S", [4, 9, 16])
+def test_state_keys(env, S):
+    rng = np.random.default_rng(S)
+    B = 2000
+    T = rng.integers(-3, 4, (B, S, S, S)) * (rng.random((B, S, S, S)) < 0.1)
+    T[10] = T[3]
+    T[11] = 0
+    keys = env.state_keys(torch.from_numpy(dense_to_slab(T)).cuda(), S).cpu().numpy().view(np.uint64)
+    assert np.array_equal(keys, orc.state_key_batch(T))
+    assert keys[10] == keys[3] and keys[11] == 0
+    assert len(set(keys.tolist())) == len({t.tobytes() for t in T.astype(np.int32)})
+
+
+@pytest.mark.parametrize("S,R,p", [(4, 7, 0.3), (9, 23, 0.08), (16, 12, 0.03)])
+def test_change_of_basis_vs_oracle_and_invariants(env, S, R, p):
+    N, shift = 60, 2
+    tok, tgt, _ = orc.demos_seeded(8, V5, P5, R, S, shift, N)
+    mats = env.sample_unimodular(N, S, seed=21, first=5, p_nonzero=p)
+    m = mats.cpu().numpy().astype(np.int64)
+    assert np.array_equal(m, orc.sample_unimodular(21, 5, N, S, p))  # sampler contract
+    assert all(round(abs(np.linalg.det(x))) == 1 for x in m.reshape(-1, S, S).astype(np.float64))  # unimodular
+    slab = torch.from_numpy(dense_to_slab(tgt)).cuda()
+    tape = torch.from_numpy(tokens_to_tape3(tok)).cuda()
+    out, tape2, flags = env.change_of_basis(slab, mats, S, tape=tape, shift=shift, shift_out=100)
+    f = flags.cpu().numpy()
+    want = np.stack([orc.change_of_basis(tgt[n], m[n, 0], m[n, 1], m[n, 2]) for n in range(N)])
+    assert np.array_equal((f & 4) != 0, (np.abs(want.reshape(N, -1) + 0.5) > 64).any(1))
+    ok = np.abs(want.reshape(N, -1)).max(1) <= 127
+    assert ok.sum() > N // 2
+    assert np.array_equal(slab_to_dense(out.cpu().numpy()[ok], S), want[ok])
+    # factors follow: u' = A u, v' = B v, w' = C w and sum u'(x)v'(x)w' = T'
+    fac = tok.reshape(N, R, 3, S) - shift
+    fac2 = tape3_to_tokens(tape2.cpu().numpy(), S).reshape(N, R, 3, S) - 100
+    for n in (0, N // 2, N - 1):
+        assert np.array_equal(fac2[n], orc.change_of_basis_factors(fac[n], m[n, 0], m[n, 1], m[n, 2]))
+        assert np.array_equal(sum(orc.uvw_to_tensor(*fac2[n, r]) for r in range(R)), want[n])
+    assert not (f & 16).any()
+    # narrow output alphabet: entries that leave [-shift, shift] are flagged
+    _, _, f2 = env.change_of_basis(slab, mats, S, tape=tape, shift=shift, shift_out=shift)
+    assert np.array_equal((f2.cpu().numpy() & 16) != 0, (np.abs(fac2) > shift).reshape(N, -1).any(1))
+
+
+def test_change_of_basis_shared_triple_and_identity(env):
+    S, N = 9, 33
+    rng = np.random.default_rng(2)
+    T = rng.integers(-2, 3, (N, S, S, S)) * (rng.random((N, S, S, S)) < 0.2)
+    slab = torch.from_numpy(dense_to_slab(T)).cuda()
+    eye = torch.eye(S, dtype=torch.int8, device="cuda").expand(3, S, S).contiguous()
+    out, flags = env.change_of_basis(slab, eye, S)
+    assert torch.equal(out, slab) and not flags.any()
+    P = np.eye(S, dtype=np.int64)[rng.permutation(S)]  # a permutation of the first mode, shared by all games
+    mats = torch.from_numpy(np.stack([P, np.eye(S, dtype=np.int64), np.eye(S, dtype=np.int64)]).astype(np.int8)).cuda()
+    out, _ = env.change_of_basis(slab, mats, S)
+    assert np.array_equal(slab_to_dense(out.cpu().numpy(), S), np.einsum("ia,nabc->nibc", P, T))
+    inv = torch.from_numpy(np.stack([P.T, np.eye(S, dtype=np.int64), np.eye(S, dtype=np.int64)]).astype(np.int8)).cuda()
+    back, _ = env.change_of_basis(out, inv, S)
+    assert torch.equal(back, slab)
