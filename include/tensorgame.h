@@ -94,6 +94,12 @@ int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_
 int tg_rollout(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out,
                uint8_t *flags, int32_t *nnz, int32_t *steps, int64_t B, int S, int shift, void *stream);
 
+/* Same fused kernel WITHOUT the freeze: all K actions are applied even if the
+ * residual passes through zero -- SyntheticDemoDataset._take_actions
+ * (datasets.py:144-153) literally. */
+int tg_replay(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out, uint8_t *flags,
+              int32_t *nnz, int64_t B, int S, int shift, void *stream);
+
 /* ---- K3: synthetic demonstrations ----------------------------------------- */
 /* Multi-step tapes are step-major: uint8 [R][N_total][TP]; `tape_step_stride`
  * is the byte distance between consecutive steps (N_total*TP), so a rank can

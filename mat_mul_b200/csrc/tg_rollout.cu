@@ -29,7 +29,7 @@ template <int S, int NT, int NST>
 __global__ void __launch_bounds__(NT)
     rollout_kernel(const int8_t *__restrict__ slab_in, const uint8_t *__restrict__ tape, long long tape_step_stride, int K,
                    int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, int32_t *__restrict__ nnz,
-                   int32_t *__restrict__ steps, long long B, int shift, int chk) {
+                   int32_t *__restrict__ steps, long long B, int shift, int chk, int freeze) {
     using C = RollCfg<S, NT, NST>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT)
     // vote on the initial state (slot 2 is the "step -1" slot)
     if (active && nzw) s_any[2 * C::TG + g] = 1;
     __syncthreads();
-    bool alive = active && s_any[2 * C::TG + g] != 0;
+    bool alive = active && (!freeze || s_any[2 * C::TG + g] != 0);
     int until = chk;
     int my_steps = 0;
 
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(NT)
             if (any & vmask) s_any[slot * C::TG + g] = 1;
         }
         __syncthreads();
-        if (alive) alive = s_any[slot * C::TG + g] != 0;
+        if (alive && freeze) alive = s_any[slot * C::TG + g] != 0;
         if (tid == 0 && t + NST < K) load_tokens(t + NST); // stage st was fully read before the barrier
     }
 
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT)
         const uint32_t sum = s_sum[q];
         flags[g0 + q] = (uint8_t)(partial_flags(sum) & ~TG_FLAG_NULL);
         nnz[g0 + q] = (int32_t)(sum & 0xFFFFu);
-        steps[g0 + q] = (int32_t)s_steps[q];
+        if (steps) steps[g0 + q] = (int32_t)s_steps[q];
     }
     if constexpr (G::GP > S * G::RP) { // keep the slab tail padding of out-of-place results zero
         if (slab_out != slab_in)
@@ -147,31 +147,46 @@ __global__ void __launch_bounds__(NT)
 
 template <int S, int NT, int NST>
 static int launch_rollout(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out,
-                          uint8_t *flags, int32_t *nnz, int32_t *steps, long long B, int shift, cudaStream_t st) {
+                          uint8_t *flags, int32_t *nnz, int32_t *steps, long long B, int shift, int freeze, cudaStream_t st) {
     using C = RollCfg<S, NT, NST>;
     const long long grid = (B + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
     const int s3 = shift * shift * shift;
     const int chk = s3 >= 64 ? 1 : 64 / s3;
     rollout_kernel<S, NT, NST><<<(int)grid, NT, C::SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B,
-                                                                     shift, chk);
+                                                                     shift, chk, freeze);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
 
 } // namespace tg
 
-extern "C" int tg_rollout(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out,
-                          uint8_t *flags, int32_t *nnz, int32_t *steps, int64_t B, int S, int shift, void *stream) {
+static int rollout_dispatch(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out,
+                            uint8_t *flags, int32_t *nnz, int32_t *steps, int64_t B, int S, int shift, int freeze,
+                            void *stream) {
     if (!tg::supported_S(S) || B < 0 || K < 0 || shift < 1 || shift > 4) return TG_E_ARG;
     if (B == 0) return TG_OK;
-    if (!slab_in || !slab_out || !flags || !nnz || !steps || (K > 0 && !tape)) return TG_E_ARG;
+    if (!slab_in || !slab_out || !flags || !nnz || (freeze && !steps) || (K > 0 && !tape)) return TG_E_ARG;
     if (((uintptr_t)slab_in | (uintptr_t)slab_out | (uintptr_t)tape | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     switch (S) {
-    case 4: return tg::launch_rollout<4, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, st);
-    case 9: return tg::launch_rollout<9, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, st);
-    case 16: return tg::launch_rollout<16, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, st);
+    case 4: return tg::launch_rollout<4, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+    case 9: return tg::launch_rollout<9, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+    case 16: return tg::launch_rollout<16, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
     }
     return TG_E_ARG;
 }
+
+extern "C" {
+
+int tg_rollout(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out, uint8_t *flags,
+               int32_t *nnz, int32_t *steps, int64_t B, int S, int shift, void *stream) {
+    return rollout_dispatch(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, S, shift, 1, stream);
+}
+
+int tg_replay(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stride, int K, int8_t *slab_out, uint8_t *flags,
+              int32_t *nnz, int64_t B, int S, int shift, void *stream) {
+    return rollout_dispatch(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, nullptr, B, S, shift, 0, stream);
+}
+
+} // extern "C"

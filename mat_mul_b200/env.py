@@ -155,6 +155,22 @@ def rollout(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: tor
     return out, flags, nnz, steps
 
 
+def replay(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: torch.Tensor | None = None):
+    """All K actions of a step-major tape applied without freezing (datasets.py:144-153).  Returns (out, flags, nnz)."""
+    _need_cuda(slab, "slab", torch.int8)
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(S)
+    B, K = slab.shape[0], tape.shape[0]
+    if tape.dim() != 3 or tape.shape[1] != B or tape.shape[2] != lay.token_pitch or slab.shape[1] != lay.game_pitch:
+        raise TensorGameError(f"expected slab (B,{lay.game_pitch}) and tape (K,B,{lay.token_pitch})")
+    out = torch.empty_like(slab) if out is None else out
+    flags = torch.empty(B, dtype=torch.uint8, device=slab.device)
+    nnz = torch.empty(B, dtype=torch.int32, device=slab.device)
+    check(_lib.lib().tg_replay(_p(slab), _p(tape), B * lay.token_pitch, K, _p(out), _p(flags), _p(nnz), B, S, shift, _stream()),
+          "tg_replay")
+    return out, flags, nnz
+
+
 # ---------------------------------------------------------------- K3
 def _cat_arrays(values, probs):
     import numpy as np

@@ -213,6 +213,30 @@ def main() -> None:
         "str_key": np.array(utils.state_to_str(torch.tensor([[1.0, -2.0], [0.0, 3.0]]))),
     }
     np.savez_compressed(OUT / "misc.npz", **misc)
+    # ---------------------------------------------------------------- MCTS trajectory (act.py:8-64) with a fake model
+    sys.path.insert(0, str(REPO))
+    from tests.fake_model import FakeAlphaTensor
+
+    mc = {}
+    for tag, S, T, max_actions, n_sim, seed in [("a", 4, 2, 4, 6, 0), ("b", 4, 1, 3, 5, 1), ("c", 9, 2, 3, 4, 2)]:
+        torch.manual_seed(100 + seed)
+        _, start = utils.create_synthetic_demo(torch.tensor((-1, 0, 1)), torch.tensor((0.1, 0.8, 0.1)), 2, S, 1)
+        init = torch.cat((start.unsqueeze(0), torch.zeros(T - 1, S, S, S)))
+        fm = FakeAlphaTensor(dim_3d=S, n_samples=4, n_logits=3, seed=seed)
+        state_seq, policy_seq, reward_seq = act.actor_prediction(fm, init, max_actions, n_sim, 100)
+        mc[f"{tag}_cfg"] = np.array([S, T, max_actions, n_sim, seed])
+        mc[f"{tag}_init"] = init.numpy().astype(np.int16)
+        mc[f"{tag}_states"] = torch.stack(state_seq).numpy().astype(np.int16)
+        mc[f"{tag}_policy"] = policy_seq.numpy()
+        mc[f"{tag}_rewards"] = reward_seq.numpy()
+        mc[f"{tag}_calls"] = np.array(fm.calls)
+    np.savez_compressed(OUT / "mcts.npz", **mc)
+
+    # ---------------------------------------------------------------- star-import surface of the three modules
+    import json
+
+    surface = {m.__name__: sorted(n for n in dir(m) if not n.startswith("_")) for m in (utils, datasets, act)}
+    (OUT / "surface.json").write_text(json.dumps(surface, indent=1))
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*.npz")):
         print(f"  {f.name}: {f.stat().st_size} B")
