@@ -38,6 +38,7 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning sweep only")
     ap.add_argument("--variant", type=int, default=0, help="tuning sweep only")
     return ap.parse_args()
@@ -93,6 +94,63 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _time_ms(fn, iters: int, torch) -> float:
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, barrier) -> dict:
+    """The other kernels of the path on the same games (per-GPU numbers, CUDA events, a few launches each):
+    demo generation (metric: demos/s), fused rollout, change of basis, training-sample batcher."""
+    import torch
+
+    B = slab.shape[0]
+    lay = env.layout(S)
+    peak, _ = hbm_peak()
+    out = {"per_gpu": True, "n_gpus": world}
+    t2, s2 = torch.empty_like(tape3), torch.empty_like(slab)
+    ms = _time_ms(lambda: env.make_synthetic_demos(B, R, S, values, probs, shift, seed=1, device=dev, tape=t2, slab=s2), 3, torch)
+    algo = S ** 3 + R * 3 * S
+    out["demo_gen"] = {"metric": "synthetic_demos_per_sec", "value": B / ms * 1e3, "ms": ms, "R": R,
+                       "algorithmic_bytes_per_demo": algo, "hbm_frac": B * algo / (ms * 1e-3) / 1e9 / peak,
+                       "bound": "issue (Philox draws + rank-1 accumulation), see DESIGN.md"}
+    ms = _time_ms(lambda: env.accumulate_demos(tape3, S, shift, slab=s2), 3, torch)
+    out["demo_accumulate"] = {"value": B / ms * 1e3, "unit": "demos/s", "ms": ms}
+    rev = tape3.flip(0).contiguous()
+    ms = _time_ms(lambda: env.rollout(slab, rev, S, shift, out=s2), 3, torch)
+    algo = 2 * S ** 3 + R * 3 * S + 8
+    out["rollout"] = {"metric": "env_steps_per_sec (fused K-step rollout)", "value": B * R / ms * 1e3, "games_per_sec": B / ms * 1e3,
+                      "K": R, "ms": ms, "hbm_frac": B * algo / (ms * 1e-3) / 1e9 / peak}
+    del rev, t2
+    nb = min(B, 1 << 18)
+    mats = env.sample_unimodular(nb, S, seed=3, p_nonzero={4: 0.3, 9: 0.08, 16: 0.03}[S], device=dev)
+    ms = _time_ms(lambda: env.change_of_basis(slab[:nb], mats, S), 3, torch)
+    algo = S ** 3 + 3 * S * S + S ** 3
+    out["change_of_basis"] = {"value": nb / ms * 1e3, "unit": "games/s", "ms": ms, "games": nb,
+                              "hbm_frac": nb * algo / (ms * 1e-3) / 1e9 / peak, "int_ops_per_game": 6 * S ** 4}
+    idx = torch.randint(0, B * R, (1 << 16,), device=dev)
+    ms = _time_ms(lambda: env.demo_samples(tape3, slab, idx, S, 2, replay_shift=shift), 3, torch)
+    out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2,
+                          "hbm_frac": idx.numel() * (2 * S ** 3 * 4) / (ms * 1e-3) / 1e9 / peak}
+    if world > 1:  # demo all-gather timed as its own phase (NVLink-bound, SURVEY.md 8e)
+        from mat_mul_b200 import dist as tgd
+
+        n_g = min(B, 1 << 18)
+        shard = slab[:n_g].contiguous()
+        barrier()
+        ms = _time_ms(lambda: tgd.gather_shards(shard, n_g * world, dim=0), 3, torch)
+        out["demo_all_gather"] = {"ms": ms, "bytes_out_per_rank": n_g * world * lay.game_pitch,
+                                  "algbw_gbs": n_g * world * lay.game_pitch / (ms * 1e-3) / 1e9}
+    return out
 
 
 def cpu_reference_leg(S: int, shift: int, seconds: float = 12.0):
@@ -179,27 +237,18 @@ def main() -> None:
     if args.variant:
         _lib.lib().tg_tune_step_variant(args.variant)
 
-    # ---- synthetic games, resident in HBM: sparse residuals in [-2,2], tokens with P(coef=0)=0.7
-    gen = torch.Generator(device=dev).manual_seed(0x5EED + rank)
-    dense = torch.randint(-2, 3, (B, S, S, S), device=dev, generator=gen, dtype=torch.int8)
-    dense *= (torch.rand((B, S, S, S), device=dev, generator=gen) < 0.3)
-    slab_a = env.new_slab(B, S, dev)
-    env.slab_view(slab_a, S).copy_(dense)
-    del dense
+    # ---- synthetic games, resident in HBM: the product's own demo generator (Philox stream keyed by the GLOBAL
+    # game index, so the union over ranks is independent of N); every game replays its own demo in reverse order
+    # (datasets.py:90-92), i.e. a genuine transition on every step; P(coef = 0) = 0.7 as in the reference
+    VALUES, PROBS, R = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05), {4: 7, 9: 23, 16: 49}[S]
+    tape3, slab_a, dflags = env.make_synthetic_demos(B, R, S, VALUES, PROBS, shift, seed=0x5EED, first_demo=rank * B, device=dev)
     slab_b = torch.empty_like(slab_a)
-    n_tapes = 4
-    tapes = []
-    for _ in range(n_tapes):
-        tk = torch.randint(0, 5, (B, 3 * S), device=dev, generator=gen)
-        tk[torch.rand((B, 3 * S), device=dev, generator=gen) < 0.625] = shift  # P(0) = 0.7
-        tapes.append(env.pack_actions(tk, S))
-        del tk
     flags = torch.empty(B, dtype=torch.uint8, device=dev)
     nnz = torch.empty(B, dtype=torch.int32, device=dev)
 
     def one_step(i: int) -> None:
         src, dst = (slab_a, slab_b) if i % 2 == 0 else (slab_b, slab_a)
-        env.step_batch(src, tapes[i % n_tapes], S, shift, out=dst, flags=flags, nnz=nnz)
+        env.step_batch(src, tape3[(R - 1 - i) % R], S, shift, out=dst, flags=flags, nnz=nnz)
 
     def barrier() -> None:
         if world > 1:
@@ -220,11 +269,13 @@ def main() -> None:
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    # keep the sampler alive long enough to see the load even for very short timed regions
+    end_flags, end_nnz = flags.clone(), nnz.clone()  # state of the games right after the timed steps
+    # keep the clock sampler under the same load for ~1 s (its period is 200 ms); results are discarded
     t_end = time.perf_counter() + max(0.0, 1.0 - ms / 1e3)
     i = 0
+    scratch_f, scratch_n = torch.empty_like(flags), torch.empty_like(nnz)
     while time.perf_counter() < t_end:
-        one_step(i); i += 1
+        env.step_batch(slab_a, tape3[i % R], S, shift, out=slab_b, flags=scratch_f, nnz=scratch_n); i += 1
         if i % 8 == 0:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
@@ -242,7 +293,7 @@ def main() -> None:
         h_slab = torch.empty((Be, lay.game_pitch), dtype=torch.int8).pin_memory()
         h_slab.copy_(slab_a[:Be])
         h_tape = torch.empty((Be, lay.token_pitch), dtype=torch.uint8).pin_memory()
-        h_tape.copy_(tapes[0][:Be])
+        h_tape.copy_(tape3[R - 1][:Be])
         h_out = torch.empty_like(h_slab).pin_memory()
         h_flags = torch.empty(Be, dtype=torch.uint8).pin_memory()
         h_nnz = torch.empty(Be, dtype=torch.int32).pin_memory()
@@ -264,6 +315,12 @@ def main() -> None:
                "d2h_bytes_per_step": Be * (lay.game_pitch + 5), "steps": Ke,
                "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks over 3 streams)"}
         del h_slab, h_tape, h_out
+
+    # ---- episode statistics: the only collective of the path (two tiny all_reduces), outside the timed region
+    from mat_mul_b200 import dist as tgd
+
+    stats = tgd.reduce_episode_stats(end_flags, end_nnz)
+    extras = None if args.no_extras else measure_extras(env, dev, S, shift, slab_a, tape3, R, VALUES, PROBS, world, barrier)
 
     if rank == 0:
         peak, peak_kind = hbm_peak()
@@ -288,6 +345,10 @@ def main() -> None:
                          "algorithmic_bytes_per_step": ALGO_BYTES[S],
                          "moved_bytes_per_step": 2 * lay.game_pitch + lay.token_pitch + 5},
             "e2e": e2e, "gpu_launches": K * world, "clocks": clocks,
+            "episode_stats": {"games": stats.games, "solved": stats.solved, "min_nnz": stats.min_nnz,
+                              "out_of_range": stats.out_of_range,
+                              "note": f"after warmup+steps = {W + K} of the demos' {R} actions, replayed in reverse", "collective": "all_reduce(SUM), all_reduce(MIN) of 5 int64"},
+            "extras": extras,
         }
         if world == 1 and not args.no_cpu:
             from oracle import tg_oracle as orc  # CPU baseline leg only (checker never on the product path)
