@@ -97,9 +97,10 @@ __global__ void __launch_bounds__(NT)
             const uint4 ut = *reinterpret_cast<const uint4 *>(tok);
             const uint32_t uw[4] = {ut.x, ut.y, ut.z, ut.w};
             uint32_t any = 0;
+            const uint32_t nvw = (uint32_t)(-vw);
 #pragma unroll
             for (int i = 0; i < S; i++) {
-                row[i] += (uint32_t)(shift - (int)((uw[i >> 2] >> (8 * (i & 3))) & 0xFFu)) * (uint32_t)vw;
+                row[i] += (uint32_t)coef_u(uw, i, shift) * nvw;
                 any |= row[i] ^ H4;
             }
             if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form

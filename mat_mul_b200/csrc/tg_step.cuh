@@ -77,6 +77,11 @@ __device__ __forceinline__ int32_t pack_vw(const uint8_t *tok, const Lane<S> &L,
     }
 }
 
+// coefficient u_i = token_i - shift from the packed u tokens: one dp4a against a one-hot byte vector
+__device__ __forceinline__ int coef_u(const uint32_t uw[4], int i, int shift) {
+    return (int)__dp4a(uw[i >> 2], 1u << (8 * (i & 3)), (uint32_t)(-shift));
+}
+
 // Partial result word of one thread for one game; summing it over the WR
 // threads of a game gives nnz (bits 0-15), #threads whose update was non-zero
 // (bits 16-23) and #threads that saw an entry outside [-64,63] (bits 24-31).
@@ -99,12 +104,12 @@ __device__ __forceinline__ uint32_t rank1_update(uint8_t *game, const uint8_t *t
     uint32_t cnt = 0, rng = 0;
     int uany = 0;
     uint32_t *col = reinterpret_cast<uint32_t *>(game) + L.c;
+    const uint32_t svw = (uint32_t)(SIGN < 0 ? -vw : vw); // SIGN * VW
 #pragma unroll
     for (int i = 0; i < S; i++) {
-        const int tu = (int)((uw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-        const int negu = SIGN < 0 ? shift - tu : tu - shift; // -u_i (step) or +u_i (accumulate)
+        const int negu = coef_u(uw, i, shift);
         uint32_t t = col[i * G::WR] ^ H4;
-        t += (uint32_t)negu * (uint32_t)vw;
+        t += (uint32_t)negu * svw;
         t ^= H4;
         col[i * G::WR] = t;
         cnt += ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & L.hv) >> 7;
