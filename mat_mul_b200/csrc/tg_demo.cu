@@ -10,64 +10,81 @@
 // all games is one contiguous tg_step operand) and the int8 slab [N][GP].
 //
 // One CTA builds a tile of TG demos:
-//   A. (throughput mode) all threads draw factor triples with Philox4x32-10,
-//      one (demo, term) pair at a time from a shared work counter, retrying
-//      rejected triples, and write the tokens into a shared-memory tape;
-//      (replay modes) the tape tile is bulk-loaded from HBM instead.
+//   A. (throughput mode) every lane runs a (pair, try) state machine over the
+//      (demo, term) pairs of the tile, claimed from a shared counter one
+//      warp-aggregated atomic at a time.  A try is ceil(3S/8) Philox4x32-10
+//      blocks (round keys are launch constants); four 15-bit draws are turned
+//      into four tokens at once: per CDF threshold two IADDs (carry into bit
+//      15 of each 16-bit lane), one PRMT that gathers the four carries as byte
+//      masks, one LOP3 that XORs the token delta in.  An accepted triple goes
+//      straight to the HBM tape and, as an "accumulate record" (packed w
+//      coefficients in integer form + u, v coefficient bytes), to shared memory;
+//      (replay modes) the records are built from the tape in HBM instead.
 //   B. S threads per demo, thread j owning the entries (i, j, 0..S-1) of every
-//      row i in registers as packed words: per term  c = u_i * v_j  and
-//      acc[i][m] += c * pack(w[4m..4m+3])  -- one IMAD per four entries, the
-//      pack(w) words shared by all (i, j) (packed arithmetic of tg_step.cuh),
-//      with a range check often enough that the packed form can never alias.
-//   C. the tile (slab + tape) leaves through TMA bulk stores.
+//      row i in registers as packed words: per term  vw = v_j * pack(w) and
+//      acc[i][m] += u_i * vw[m]  -- one IMAD per four entries.  The packed sum is
+//      exact modulo 2^32 whatever the intermediate values, so only the FINAL
+//      entries matter: with R * shift^3 <= 191 a final entry outside int8
+//      always decodes outside [-64, 63] and raises TG_FLAG_RANGE; for larger
+//      R * shift^3 a per-thread bound shift^2 * sum_r |v_rj| guards the packed
+//      path and the (rare) thread above it recomputes its entries one by one.
+//   C. the slab tile leaves through one TMA bulk store.
 #include "tg_step.cuh"
 
 namespace tg {
 
+// Launch constants of the sampler (kernel parameter => constant bank operands).
 struct Categorical {
-    uint32_t thr[8];   // 16-bit CDF thresholds (65536 = never exceeded)
-    uint32_t lut_lo;   // token (value + shift) of buckets 0-3, one byte each
-    uint32_t lut_hi;   // buckets 4-7
-    uint32_t zero_pat; // token of the value 0 in every byte (0xFFFFFFFF if 0 is not in the alphabet)
-    uint32_t top_tok;  // token of the last bucket (forced unit triple)
-    int n;
+    uint32_t cadd[7];   // (0x8000 - thr15[i]) in both 16-bit lanes; thr15[i] = floor(cdf_i * 2^15)
+    uint32_t xlut[7];   // (token of bucket i+1) ^ (token of bucket i), in every byte
+    uint32_t lut0;      // token (value + shift) of bucket 0, in every byte
+    uint32_t zero_pat;  // token of the value 0 in every byte (0xFFFFFFFF if 0 is not in the alphabet)
+    uint32_t top_tok;   // token of the last bucket (forced unit triple)
+    uint32_t rk[10][2]; // Philox round keys: key + round * (0x9E3779B9, 0xBB67AE85)
 };
 
 // one Philox4x32-10 block; IMAD.WIDE gives hi and lo of each product in one instruction
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const Categorical &cat,
+                                              uint32_t out[4]) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
         const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
-        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ cat.rk[r][0];
         c1 = (uint32_t)p1;
-        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ cat.rk[r][1];
         c3 = (uint32_t)p0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
 
-template <int S, int NT, int NPASS>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+template <int S, int NT>
 struct DemoCfg {
     using G = Geo<S>;
-    static constexpr int GPASS = NT / S;  // S threads per demo (thread = factor index j)
-    static constexpr int TG = GPASS * NPASS;
-    static constexpr int ACTIVE = GPASS * S;
-    static constexpr int KW = (S + 3) / 4; // packed words per (i, j) run of S entries
+    static constexpr int TG = NT / S;      // demos per CTA; S threads per demo in phase B (thread = factor index j)
+    static constexpr int ACTIVE = TG * S;
+    static constexpr int KW = (S + 3) / 4;       // packed words per run of S entries (one (i, j), k = 0..S-1)
+    static constexpr int NCW = (2 * S + 3) / 4;  // words holding the u and v coefficient bytes
+    static constexpr int NW = (3 * S + 3) / 4;   // token words of one action
+    static constexpr int REC = G::TP;            // accumulate record: KW words pack(w) + NCW words coefficient bytes
+    static_assert(4 * (KW + NCW) <= REC, "record does not fit the token pitch");
     static constexpr int SLAB_BYTES = TG * G::GP;
-    static __host__ __device__ constexpr int tape_bytes(int R) { return R * TG * G::TP; }
-    static __host__ __device__ constexpr int smem_bytes(int R) { return SLAB_BYTES + tape_bytes(R) + TG * 4 + 16; }
+    static __host__ __device__ constexpr int rec_bytes(int R) { return R * TG * REC; }
+    static __host__ __device__ constexpr int smem_bytes(int R) { return SLAB_BYTES + rec_bytes(R) + TG * 4 + 16; }
 };
 
 // "is this factor all zero" over packed token words: OR of (word ^ zero_pat) under the factor's byte mask
 template <int S>
-__device__ __forceinline__ bool factor_nonzero(const uint32_t words[Geo<S>::TP / 4], int f, uint32_t zero_pat) {
+__device__ __forceinline__ bool factor_nonzero(const uint32_t words[(3 * S + 3) / 4], int f, uint32_t zero_pat) {
     uint32_t acc = 0;
 #pragma unroll
-    for (int w = 0; w < Geo<S>::TP / 4; w++) {
+    for (int w = 0; w < (3 * S + 3) / 4; w++) {
         uint32_t m = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -79,32 +96,29 @@ __device__ __forceinline__ bool factor_nonzero(const uint32_t words[Geo<S>::TP /
     return acc != 0;
 }
 
-// draw one factor triple (3S tokens) for (demo key k0/k1/d_lo, term r, try t); true if accepted.
-// Draw q is the 16-bit half (q & 1) of word (q >> 1) & 3 of Philox block q >> 3; bucket = number of
-// thresholds <= draw; four bucket indexes form a PRMT selector that looks the four tokens up at once.
+// Draw one factor triple (3S tokens) for demo (d_lo, d_hi), term r, try t; true if accepted.
+// Draw q is the 15-bit value in half (q & 1) of word (q >> 1) & 3 of Philox block q >> 3 with
+// ctr = (d_lo, d_hi, r | t << 16, q >> 3); bucket = number of thresholds <= draw.  Four draws at a time:
+// x + (0x8000 - thr) carries into bit 15 of its 16-bit lane iff x >= thr, PRMT (sign-replicating
+// selector) turns the four carries into byte masks, and the token of bucket b is
+// lut[0] ^ xlut[0] ^ ... ^ xlut[b-1].
 template <int S, int NTHR>
-__device__ __forceinline__ bool draw_triple(uint32_t words[Geo<S>::TP / 4], uint32_t k0, uint32_t k1, uint32_t d_lo,
-                                            int r, int t, const Categorical &cat) {
-    using G = Geo<S>;
+__device__ __forceinline__ bool draw_triple(uint32_t words[(3 * S + 3) / 4], uint32_t d_lo, uint32_t d_hi, int r, int t,
+                                            const Categorical &cat) {
     constexpr int NB = (3 * S + 7) / 8;
-#pragma unroll
-    for (int w = 0; w < G::TP / 4; w++) words[w] = 0;
+    constexpr int NW = (3 * S + 3) / 4;
 #pragma unroll
     for (int bq = 0; bq < NB; bq++) {
         uint32_t blk[4];
-        philox4x32_10((uint32_t)bq, (uint32_t)t, (uint32_t)r, d_lo, k0, k1, blk);
+        philox4x32_10(d_lo, d_hi, (uint32_t)r | ((uint32_t)t << 16), (uint32_t)bq, cat, blk);
 #pragma unroll
         for (int half = 0; half < 2; half++) { // tokens 8bq + 4half .. +3  ->  token word 2bq + half
-            if (8 * bq + 4 * half < 3 * S) {
-                uint32_t sel = 0;
+            if (2 * bq + half < NW) {
+                const uint32_t xa = blk[2 * half] & 0x7FFF7FFFu, xb = blk[2 * half + 1] & 0x7FFF7FFFu;
+                uint32_t tokw = cat.lut0;
 #pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const uint32_t wv = blk[2 * half + (h >> 1)];
-                    const uint32_t x = (h & 1) ? (wv >> 16) : (wv & 0xFFFFu);
-#pragma unroll
-                    for (int i = 0; i < NTHR; i++) sel += (x >= cat.thr[i]) ? (1u << (4 * h)) : 0u;
-                }
-                uint32_t tokw = __byte_perm(cat.lut_lo, cat.lut_hi, sel);
+                for (int i = 0; i < NTHR; i++)
+                    tokw ^= prmt(xa + cat.cadd[i], xb + cat.cadd[i], 0xFDB9u) & cat.xlut[i];
                 const int q0 = 8 * bq + 4 * half;
                 if (q0 + 4 > 3 * S) tokw &= 0xFFFFFFFFu >> (8 * (q0 + 4 - 3 * S)); // tape padding stays zero
                 words[2 * bq + half] = tokw;
@@ -115,155 +129,220 @@ __device__ __forceinline__ bool draw_triple(uint32_t words[Geo<S>::TP / 4], uint
            factor_nonzero<S>(words, 2, cat.zero_pat);
 }
 
-template <int S, int NT, int NPASS, bool SAMPLE, int NTHR>
+// token words of one action -> accumulate record: pack(w) in integer form (sum_b (w_b - shift) 256^b per word,
+// bytes beyond S contribute 0) followed by the u, v coefficient bytes (token - shift as int8)
+template <int S, int NT>
+__device__ __forceinline__ void emit_record(const uint32_t words[(3 * S + 3) / 4], int shift, uint32_t *rec) {
+    using C = DemoCfg<S, NT>;
+    constexpr int o = 2 * S;
+    constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu;
+    const uint32_t sh4 = (uint32_t)shift * ONES4;
+    uint32_t out[C::REC / 4];
+#pragma unroll
+    for (int m = 0; m < C::REC / 4; m++) out[m] = 0;
+#pragma unroll
+    for (int m = 0; m < C::KW; m++) {
+        const uint32_t lo = words[(o >> 2) + m];
+        uint32_t wt = lo;
+        if constexpr ((o & 3) != 0) {
+            const uint32_t hi = ((o >> 2) + m + 1 < C::NW) ? words[(o >> 2) + m + 1] : 0u;
+            wt = __funnelshift_r(lo, hi, 8 * (o & 3));
+        }
+        const uint32_t msk = (m == C::KW - 1) ? WLAST : 0xFFFFFFFFu;
+        out[m] = (wt & msk) - (sh4 & msk);
+    }
+#pragma unroll
+    for (int m = 0; m < C::NCW; m++) out[C::KW + m] = ((words[m] | H4) - sh4) ^ H4;
+    if constexpr (C::REC % 16 == 0) {
+#pragma unroll
+        for (int m = 0; m < C::REC / 16; m++)
+            reinterpret_cast<uint4 *>(rec)[m] = make_uint4(out[4 * m], out[4 * m + 1], out[4 * m + 2], out[4 * m + 3]);
+    }
+}
+
+// sign-extended byte b of a coefficient word
+template <int B>
+__device__ __forceinline__ int coef_byte(uint32_t w) {
+    constexpr uint32_t sel = (uint32_t)B | ((uint32_t)(B | 8) << 4) | ((uint32_t)(B | 8) << 8) | ((uint32_t)(B | 8) << 12);
+    return (int)prmt(w, 0u, sel);
+}
+
+template <int S, int NT, bool SAMPLE, int NTHR, bool GUARD>
 __global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
-    demo_kernel(unsigned long long seed, unsigned long long first_demo, long long N, int R, int shift, Categorical cat,
-                int max_tries, int chk, uint8_t *__restrict__ tape, long long tape_step_stride, int8_t *__restrict__ slab,
-                uint8_t *__restrict__ flags) {
-    using C = DemoCfg<S, NT, NPASS>;
+    demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
+                const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
+                long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags) {
+    using C = DemoCfg<S, NT>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_slab = smem;
-    uint8_t *s_tape = smem + C::SLAB_BYTES;                                  // [R][TG][TP]
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_tape + C::tape_bytes(R)); // [TG]
+    uint8_t *s_rec = smem + C::SLAB_BYTES;                                    // [R][TG][REC]
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_rec + C::rec_bytes(R)); // [TG]
     uint32_t *s_work = s_flag + C::TG;
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_work + 2);
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const long long g0 = (long long)blockIdx.x * C::TG;
     const int ng = (int)min((long long)C::TG, N - g0);
+    const int npairs = ng * R;
 
-    for (int w = tid; w < C::SLAB_BYTES / 4; w += NT) reinterpret_cast<uint32_t *>(s_slab)[w] = 0;
     for (int g = tid; g < C::TG; g += NT) s_flag[g] = 0;
-    if (tid == 0) {
-        *s_work = 0;
-        if constexpr (!SAMPLE) {
-            mbar_init(s_bar, 1);
-            mbar_fence_init();
-        }
-    }
+    if (tid == 0) *s_work = 0;
     __syncthreads();
 
     if constexpr (SAMPLE) {
-        // ---------------- A. draw the factor triples of the tile.  Every lane runs a small state machine
-        // (pair, try): a rejected triple just bumps the try, an accepted one is stored and the lane claims the
-        // next pair from the shared counter -- so lanes never wait for another lane's rejection loop.
-        const int npairs = ng * R;
-        int p = (int)atomicAdd(s_work, 1u), t = 0;
-        int g = 0, r = 0;
-        uint32_t k0 = 0, d_lo = 0;
-        const uint32_t k1 = (uint32_t)(seed >> 32);
-        auto claim = [&]() {
+        // ---------------- A. draw the factor triples of the tile.  A rejected triple just bumps the lane's try,
+        // an accepted one is stored and the lane takes the next pair -- lanes never wait for another lane's
+        // rejection loop; pairs are handed out with one atomic per warp and round.
+        int p = npairs, t = 0, g = 0, r = 0;
+        uint32_t d_lo = 0, d_hi = 0;
+        bool need = true;
+        while (true) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = (int)atomicAdd(s_work, (uint32_t)__popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (need) {
+                    p = base + __popc(m & ((1u << lane) - 1u));
+                    t = 0, need = false;
+                    if (p < npairs) {
+                        g = magic_r ? (int)__umulhi((uint32_t)p, magic_r) : p; // p / R  (p * R < 2^32; magic 0 <=> R == 1)
+                        r = p - g * R;
+                        const unsigned long long d = first_demo + (unsigned long long)(g0 + g);
+                        d_lo = (uint32_t)d, d_hi = (uint32_t)(d >> 32);
+                    }
+                }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, p < npairs) == 0) break;
             if (p < npairs) {
-                g = p / R, r = p - g * R;
-                const unsigned long long d = first_demo + (unsigned long long)(g0 + g);
-                k0 = (uint32_t)seed ^ ((uint32_t)(d >> 32) * 0x9E3779B9u), d_lo = (uint32_t)d;
-            }
-        };
-        claim();
-        while (p < npairs) {
-            uint32_t words[G::TP / 4];
-            bool ok = draw_triple<S, NTHR>(words, k0, k1, d_lo, r, t, cat);
-            if (!ok && t + 1 >= max_tries) { // bounded retries: forced unit triple (the reference would loop forever, Q11)
+                uint32_t words[G::TP / 4];
 #pragma unroll
-                for (int w = 0; w < G::TP / 4; w++) words[w] = 0;
+                for (int w = C::NW; w < G::TP / 4; w++) words[w] = 0;
+                bool ok = draw_triple<S, NTHR>(words, d_lo, d_hi, r, t, cat);
+                if (!ok && t + 1 >= max_tries) { // bounded retries: forced unit triple (the reference would loop forever, Q11)
 #pragma unroll
-                for (int q = 0; q < 3 * S; q++)
-                    words[q >> 2] |= (((q % S) == 0 ? cat.top_tok : (uint32_t)shift) & 0xFFu) << (8 * (q & 3));
-                atomicOr(&s_flag[g], 8u);
-                ok = true;
-            }
-            if (ok) {
-                uint32_t *dst = reinterpret_cast<uint32_t *>(s_tape + ((size_t)r * C::TG + g) * G::TP);
+                    for (int w = 0; w < C::NW; w++) words[w] = 0;
 #pragma unroll
-                for (int w = 0; w < G::TP / 4; w++) dst[w] = words[w];
-                p = (int)atomicAdd(s_work, 1u), t = 0;
-                claim();
-            } else {
-                t++;
+                    for (int q = 0; q < 3 * S; q++)
+                        words[q >> 2] |= (((q % S) == 0 ? cat.top_tok : (uint32_t)shift) & 0xFFu) << (8 * (q & 3));
+                    atomicOr(&s_flag[g], (uint32_t)TG_FLAG_EXHAUSTED);
+                    ok = true;
+                }
+                if (ok) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(tape + (size_t)r * tape_step_stride + (g0 + g) * G::TP);
+#pragma unroll
+                    for (int w = 0; w < G::TP / 16; w++)
+                        dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
+                    emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)r * C::TG + g) * C::REC));
+                    need = true;
+                } else {
+                    t++;
+                }
             }
         }
     } else {
-        // ---------------- A'. replay: bulk-load the tape tile [R][ng][TP]
-        if (tid == 0) {
-            mbar_expect_tx(s_bar, (uint32_t)(R * ng * G::TP));
-            for (int r = 0; r < R; r++)
-                bulk_g2s(s_tape + (size_t)r * C::TG * G::TP, tape + (size_t)r * tape_step_stride + g0 * G::TP,
-                         (uint32_t)(ng * G::TP), s_bar);
+        // ---------------- A'. replay: build the records from the tape in HBM
+        for (int p = tid; p < npairs; p += NT) {
+            const int g = magic_r ? (int)__umulhi((uint32_t)p, magic_r) : p;
+            const int r = p - g * R;
+            const uint4 *src = reinterpret_cast<const uint4 *>(tape + (size_t)r * tape_step_stride + (g0 + g) * G::TP);
+            uint32_t words[G::TP / 4];
+#pragma unroll
+            for (int w = 0; w < G::TP / 16; w++) {
+                const uint4 q = src[w];
+                words[4 * w] = q.x, words[4 * w + 1] = q.y, words[4 * w + 2] = q.z, words[4 * w + 3] = q.w;
+            }
+            emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)r * C::TG + g) * C::REC));
         }
-        mbar_wait(s_bar, 0);
     }
     __syncthreads();
 
     // ---------------- B. accumulate the R rank-1 terms in registers
     constexpr int KW = C::KW;
-    const bool active = tid < C::ACTIVE;
-    const int gl = tid / S, j = tid % S;
-    const int vword = ((S + j) >> 2) * 4;                 // aligned word of the tape holding v_j
-    const uint32_t vhot = 1u << (8 * ((S + j) & 3));      // one-hot selector of v_j inside it
-    constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu; // valid bytes of the last w word
-#pragma unroll 1
-    for (int p = 0; p < NPASS; p++) {
-        const int g = p * C::GPASS + gl;
-        if (active && g < ng) {
-            int32_t acc[S][KW];
+    const int g = tid / S, j = tid % S;
+    constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu; // valid bytes of the last word
+    if (tid < C::ACTIVE && g < ng) {
+        int32_t acc[S][KW];
 #pragma unroll
-            for (int i = 0; i < S; i++)
+        for (int i = 0; i < S; i++)
 #pragma unroll
-                for (int m = 0; m < KW; m++) acc[i][m] = 0;
-            uint32_t bad = 0;
-            int until = chk;
-            for (int r = 0; r < R; r++) {
-                const uint8_t *tok = s_tape + ((size_t)r * C::TG + g) * G::TP;
-                const uint32_t *tw = reinterpret_cast<const uint32_t *>(tok);
-                // packed w coefficients, bytes 2S .. 3S-1 of the tape record (funnel shift when not word aligned)
-                int32_t wp[KW];
+            for (int m = 0; m < KW; m++) acc[i][m] = 0;
+        int bound = 0;
+        const uint8_t *rec0 = s_rec + (size_t)g * C::REC;
+        const int voff = 4 * KW + S + j; // byte offset of v_j in the record
+#pragma unroll 2
+        for (int r = 0; r < R; r++) {
+            const uint8_t *rec = rec0 + (size_t)r * (C::TG * C::REC);
+            uint32_t q[C::REC / 4];
 #pragma unroll
-                for (int m = 0; m < KW; m++) {
-                    constexpr int o = 2 * S;
-                    const uint32_t lo = tw[(o >> 2) + m];
-                    uint32_t wt = lo;
-                    if constexpr ((o & 3) != 0) wt = __funnelshift_r(lo, tw[(o >> 2) + m + 1], 8 * (o & 3));
-                    const uint32_t msk = (m == KW - 1) ? WLAST : 0xFFFFFFFFu;
-                    wp[m] = (int32_t)((wt & msk) - (((uint32_t)shift * ONES4) & msk));
-                }
-                const int vj = (int)__dp4a(*reinterpret_cast<const uint32_t *>(tok + vword), vhot, (uint32_t)(-shift));
-                const uint4 ut = *reinterpret_cast<const uint4 *>(tok);
-                const uint32_t uw[4] = {ut.x, ut.y, ut.z, ut.w};
-#pragma unroll
-                for (int i = 0; i < S; i++) {
-                    const int cij = coef_u(uw, i, shift) * vj;
-#pragma unroll
-                    for (int m = 0; m < KW; m++) acc[i][m] += cij * wp[m];
-                }
-                if (--until == 0 || r == R - 1) { // every entry still in [-64,63]? then the next chk terms cannot alias
-                    until = chk;
-#pragma unroll
-                    for (int i = 0; i < S; i++)
-#pragma unroll
-                        for (int m = 0; m < KW; m++) {
-                            const uint32_t ob = (uint32_t)acc[i][m] + H4;
-                            bad |= ~(ob ^ (ob << 1)) & ((m == KW - 1) ? (WLAST & H4) : H4);
-                        }
-                }
+            for (int m = 0; m < C::REC / 16; m++) {
+                const uint4 v4 = reinterpret_cast<const uint4 *>(rec)[m];
+                q[4 * m] = v4.x, q[4 * m + 1] = v4.y, q[4 * m + 2] = v4.z, q[4 * m + 3] = v4.w;
             }
-            // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k
-            uint8_t *gbase = s_slab + (size_t)g * G::GP + j * S;
+            const int vj = (int)reinterpret_cast<const int8_t *>(rec)[voff];
+            if constexpr (GUARD) bound += abs(vj);
+            int32_t vw[KW];
+#pragma unroll
+            for (int m = 0; m < KW; m++) vw[m] = vj * (int32_t)q[m];
 #pragma unroll
             for (int i = 0; i < S; i++) {
-                if constexpr (S % 4 == 0) {
+                int ui;
+                switch (i & 3) {
+                case 0: ui = coef_byte<0>(q[KW + (i >> 2)]); break;
+                case 1: ui = coef_byte<1>(q[KW + (i >> 2)]); break;
+                case 2: ui = coef_byte<2>(q[KW + (i >> 2)]); break;
+                default: ui = coef_byte<3>(q[KW + (i >> 2)]); break;
+                }
 #pragma unroll
-                    for (int m = 0; m < KW; m++)
-                        reinterpret_cast<uint32_t *>(gbase + i * G::RP)[m] = ((uint32_t)acc[i][m] + H4) ^ H4;
-                } else {
+                for (int m = 0; m < KW; m++) acc[i][m] += ui * vw[m];
+            }
+        }
+        uint32_t bad = 0;
+        uint8_t *gbase = s_slab + (size_t)g * G::GP + j * S;
+        if (GUARD && bound * shift * shift > 191) {
+            // a final entry might alias inside the packed words: recompute this thread's entries one by one
+#pragma unroll 1
+            for (int i = 0; i < S; i++)
+#pragma unroll 1
+                for (int k = 0; k < S; k++) {
+                    int e = 0;
+                    for (int r = 0; r < R; r++) {
+                        const uint8_t *rec = rec0 + (size_t)r * (C::TG * C::REC);
+                        const int8_t *cb = reinterpret_cast<const int8_t *>(rec) + 4 * KW;
+                        const uint32_t wb = (reinterpret_cast<const uint32_t *>(rec)[k >> 2] + H4) ^ H4; // integer form -> bytes
+                        e += (int)cb[i] * (int)cb[S + j] * (int)(int8_t)((wb >> (8 * (k & 3))) & 0xFFu);
+                    }
+                    if (e < -64 || e > 63) bad = 1;
+                    gbase[i * G::RP + k] = (uint8_t)e;
+                }
+        } else {
+            // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k
 #pragma unroll
-                    for (int k = 0; k < S; k++) {
-                        const uint32_t t = ((uint32_t)acc[i][k >> 2] + H4) ^ H4;
-                        gbase[i * G::RP + k] = (uint8_t)(t >> (8 * (k & 3)));
+            for (int i = 0; i < S; i++) {
+#pragma unroll
+                for (int m = 0; m < KW; m++) {
+                    const uint32_t t = ((uint32_t)acc[i][m] + H4) ^ H4;
+                    bad |= (t ^ (t << 1)) & ((m == KW - 1) ? (WLAST & H4) : H4);
+                    if constexpr (S % 4 == 0) {
+                        reinterpret_cast<uint32_t *>(gbase + i * G::RP)[m] = t;
+                    } else {
+#pragma unroll
+                        for (int k = 4 * m; k < S && k < 4 * m + 4; k++) gbase[i * G::RP + k] = (uint8_t)(t >> (8 * (k & 3)));
                     }
                 }
             }
-            if (bad) atomicOr(&s_flag[g], (uint32_t)TG_FLAG_RANGE);
+        }
+        if (bad) atomicOr(&s_flag[g], (uint32_t)TG_FLAG_RANGE);
+    }
+    // row / game padding of the tile is zero (slab contract)
+    if constexpr (G::RP != G::S2 || G::GP != S * G::RP) {
+        constexpr int PADR = G::RP - G::S2, PADG = G::GP - S * G::RP;
+        for (int e = tid; e < ng * (S * PADR + PADG); e += NT) {
+            const int gg = e / (S * PADR + PADG), x = e % (S * PADR + PADG);
+            const int off = x < S * PADR ? (x / (PADR ? PADR : 1)) * G::RP + G::S2 + x % (PADR ? PADR : 1) : S * G::RP + (x - S * PADR);
+            s_slab[(size_t)gg * G::GP + off] = 0;
         }
     }
     fence_proxy_async();
@@ -272,44 +351,43 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
     // ---------------- C. tile out
     if (tid == 0) {
         bulk_s2g(slab + g0 * G::GP, s_slab, (uint32_t)(ng * G::GP));
-        if constexpr (SAMPLE) {
-            for (int r = 0; r < R; r++)
-                bulk_s2g(tape + (size_t)r * tape_step_stride + g0 * G::TP, s_tape + (size_t)r * C::TG * G::TP,
-                         (uint32_t)(ng * G::TP));
-        }
         bulk_commit();
     }
     if (flags)
-        for (int g = tid; g < ng; g += NT) flags[g0 + g] = (uint8_t)s_flag[g];
+        for (int gg = tid; gg < ng; gg += NT) flags[g0 + gg] = (uint8_t)s_flag[gg];
     if (tid == 0) bulk_wait<0>();
 }
 
-template <int S, int NT, int NPASS, bool SAMPLE, int NTHR>
-static int launch_demo(unsigned long long seed, unsigned long long first, long long N, int R, int shift,
-                       const Categorical &cat, int max_tries, uint8_t *tape, long long stride, int8_t *slab,
-                       uint8_t *flags, cudaStream_t st) {
-    using C = DemoCfg<S, NT, NPASS>;
-    auto kern = demo_kernel<S, NT, NPASS, SAMPLE, NTHR>;
+template <int S, int NT, bool SAMPLE, int NTHR>
+static int launch_demo(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
+                       uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
+    using C = DemoCfg<S, NT>;
     const int smem = C::smem_bytes(R);
-    if (smem > 227 * 1024) return TG_E_ARG;
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int s3 = shift * shift * shift;
-    const int chk = s3 >= 64 ? 1 : 64 / s3;
+    if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
+    const bool guard = (long long)R * shift * shift * shift > 191;
+    const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R); // ceil(2^32 / R)
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
-    kern<<<(int)grid, NT, smem, st>>>(seed, first, N, R, shift, cat, max_tries, chk, tape, stride, slab, flags);
+    if (guard) {
+        auto kern = demo_kernel<S, NT, SAMPLE, NTHR, true>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
+    } else {
+        auto kern = demo_kernel<S, NT, SAMPLE, NTHR, false>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
+    }
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
 
 template <bool SAMPLE, int NTHR>
-static int dispatch_demo(unsigned long long seed, unsigned long long first, long long N, int R, int S, int shift,
-                         const Categorical &cat, int max_tries, uint8_t *tape, long long stride, int8_t *slab,
-                         uint8_t *flags, cudaStream_t st) {
+static int dispatch_demo(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
+                         int max_tries, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     switch (S) {
-    case 4: return launch_demo<4, 256, 1, SAMPLE, NTHR>(seed, first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    case 9: return launch_demo<9, 256, 1, SAMPLE, NTHR>(seed, first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    case 16: return launch_demo<16, 256, 1, SAMPLE, NTHR>(seed, first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    case 4: return launch_demo<4, 256, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    case 9: return launch_demo<9, 256, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    case 16: return launch_demo<16, 256, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
     }
     return TG_E_ARG;
 }
@@ -321,7 +399,8 @@ extern "C" {
 int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int S, int shift, const int8_t *values,
                        const double *probs, int n_values, int max_tries, uint8_t *tape, int64_t tape_step_stride,
                        int8_t *slab, uint8_t *flags, void *stream) {
-    if (!tg::supported_S(S) || N < 0 || R < 1 || shift < 1 || shift > 4 || n_values < 1 || n_values > 8 || max_tries < 1)
+    if (!tg::supported_S(S) || N < 0 || R < 1 || shift < 1 || shift > 4 || n_values < 1 || n_values > 8 || max_tries < 1 ||
+        max_tries > 65535)
         return TG_E_ARG;
     if (N == 0) return TG_OK;
     if (!values || !probs || !tape || !slab) return TG_E_ARG;
@@ -333,26 +412,33 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
         total += probs[i];
     }
     if (!(total > 0)) return TG_E_ARG;
-    uint8_t lut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cat.zero_pat = 0xFFFFFFFFu;
-    for (int i = 0; i < 8; i++) cat.thr[i] = 65536u;
+    uint32_t prev = 0;
     for (int i = 0; i < n_values; i++) {
+        const uint32_t tok = (uint32_t)(values[i] + shift) & 0xFFu;
+        if (i == 0) cat.lut0 = tok * tg::ONES4;
+        if (i > 0) {
+            // bucket >= i  <=>  draw >= thr15[i-1] = floor(cdf_{i-1} * 2^15); 32768 is never reached
+            const double t = run * 32768.0;
+            const uint32_t thr = t >= 32768.0 ? 32768u : (uint32_t)t;
+            cat.cadd[i - 1] = (0x8000u - thr) * 0x00010001u;
+            cat.xlut[i - 1] = (tok ^ prev) * tg::ONES4;
+        }
         run += probs[i] / total;
-        const double t = run * 65536.0;
-        cat.thr[i] = (i == n_values - 1 || t >= 65536.0) ? 65536u : (uint32_t)t;
-        lut[i] = (uint8_t)(values[i] + shift);
-        if (values[i] == 0) cat.zero_pat = (uint32_t)shift * 0x01010101u;
+        prev = tok;
+        if (values[i] == 0) cat.zero_pat = (uint32_t)shift * tg::ONES4;
     }
-    cat.lut_lo = lut[0] | (lut[1] << 8) | (lut[2] << 16) | ((uint32_t)lut[3] << 24);
-    cat.lut_hi = lut[4] | (lut[5] << 8) | (lut[6] << 16) | ((uint32_t)lut[7] << 24);
-    cat.top_tok = lut[n_values - 1];
-    cat.n = n_values;
+    cat.top_tok = prev;
+    for (int r = 0; r < 10; r++) {
+        cat.rk[r][0] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        cat.rk[r][1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (n_values <= 3)
-        return tg::dispatch_demo<true, 2>(seed, first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
+        return tg::dispatch_demo<true, 2>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
     if (n_values <= 5)
-        return tg::dispatch_demo<true, 4>(seed, first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
-    return tg::dispatch_demo<true, 7>(seed, first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
+        return tg::dispatch_demo<true, 4>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
+    return tg::dispatch_demo<true, 7>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
 }
 
 int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,
@@ -362,8 +448,8 @@ int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N,
     if (!tape || !slab) return TG_E_ARG;
     if (((uintptr_t)tape | (uintptr_t)slab | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
     tg::Categorical cat = {};
-    return tg::dispatch_demo<false, 2>(0, 0, N, R, S, shift, cat, 1, const_cast<uint8_t *>(tape), tape_step_stride, slab,
-                                       flags, (cudaStream_t)stream);
+    return tg::dispatch_demo<false, 2>(0, N, R, S, shift, cat, 1, const_cast<uint8_t *>(tape), tape_step_stride, slab, flags,
+                                       (cudaStream_t)stream);
 }
 
 } // extern "C"

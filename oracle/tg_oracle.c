@@ -585,24 +585,24 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
 }
 
-/* Integer CDF for the device sampler: thr[i] = floor(cdf_i * 2^16) with the
- * float64 running sum of probs/sum; a 16-bit draw x picks the first i < n-1
- * with x < thr[i]; the last bucket catches everything. */
+/* Integer CDF for the device sampler: thr[i] = floor(cdf_i * 2^15) with the
+ * float64 running sum of probs/sum; a 15-bit draw x picks the first i < n-1
+ * with x < thr[i]; the last bucket catches everything (32768 = never). */
 void orc_philox_thresholds(const double *probs, int n, uint32_t *thr) {
     double total = 0, run = 0;
     for (int i = 0; i < n; i++) total += probs[i];
     for (int i = 0; i < n; i++) {
         run += probs[i] / total;
-        double t = run * 65536.0;
-        thr[i] = (i == n - 1 || t >= 65536.0) ? 65536u : (uint32_t)t;
+        double t = run * 32768.0;
+        thr[i] = (i == n - 1 || t >= 32768.0) ? 32768u : (uint32_t)t;
     }
 }
 
 /* Throughput-mode demo contract (ours).  For demo d (global index), term r,
- * try t, the 3S coefficient draws q = 0..3S-1 are 16-bit halves of the Philox
+ * try t, the 3S coefficient draws q = 0..3S-1 are 15-bit values of the Philox
  * stream: block bq = q / 8 with
- *   ctr = (bq , t , r , d_lo) , key = (seed_lo ^ d_hi * 0x9E3779B9 , seed_hi),
- * word (q / 2) % 4 of the block, low half for even q, high half for odd q;
+ *   ctr = (d_lo , d_hi , r | t << 16 , bq) , key = (seed_lo , seed_hi),
+ * word (q / 2) % 4 of the block, bits 0-14 for even q, bits 16-30 for odd q;
  * draw x -> first i < n-1 with x < thr[i], else n-1.  A try is rejected iff u,
  * v or w is all zero (utils.py:229); at most max_tries tries, after which the
  * term is forced to the unit triple (u=v=w=e_0 * values[n-1]) and *exhausted
@@ -614,7 +614,7 @@ void orc_demo_philox(uint64_t seed, uint64_t d, const int32_t *values, const uin
     const int S3 = S * S * S;
     int32_t tmp[4096];
     memset(target_out, 0, sizeof(int32_t) * S3);
-    uint32_t key[2] = {(uint32_t)seed ^ ((uint32_t)(d >> 32) * 0x9E3779B9u), (uint32_t)(seed >> 32)};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     for (int r = 0; r < R; r++) {
         int32_t f[3][64];
         int ok = 0;
@@ -623,11 +623,11 @@ void orc_demo_philox(uint64_t seed, uint64_t d, const int32_t *values, const uin
             uint32_t blk[4];
             for (int q = 0; q < 3 * S; q++) {
                 if ((q & 7) == 0) {
-                    uint32_t ctr[4] = {(uint32_t)(q >> 3), (uint32_t)t, (uint32_t)r, (uint32_t)d};
+                    uint32_t ctr[4] = {(uint32_t)d, (uint32_t)(d >> 32), (uint32_t)r | ((uint32_t)t << 16), (uint32_t)(q >> 3)};
                     orc_philox4x32_10(ctr, key, blk);
                 }
                 uint32_t word = blk[(q >> 1) & 3];
-                uint32_t x = (q & 1) ? (word >> 16) : (word & 0xFFFFu);
+                uint32_t x = ((q & 1) ? (word >> 16) : word) & 0x7FFFu;
                 int i = 0;
                 while (i < n_values - 1 && x >= thr[i]) i++;
                 int32_t val = values[i];
