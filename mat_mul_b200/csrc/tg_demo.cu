@@ -74,9 +74,17 @@ struct DemoCfg {
     static constexpr int NW = (3 * S + 3) / 4;   // token words of one action
     static constexpr int REC = G::TP;            // accumulate record: KW words pack(w) + NCW words coefficient bytes
     static_assert(4 * (KW + NCW) <= REC, "record does not fit the token pitch");
-    static constexpr int SLAB_BYTES = TG * G::GP;
+    // pitch of a game in the shared-memory tile: padded so that the lanes of neighbouring demos in a warp store to
+    // different banks (768 B and 64 B pitches are 0 mod 128 / alias every other demo); each game leaves with its
+    // own bulk store
+    static constexpr int PITCH = G::GP + (S == 9 ? 32 : (S == 4 ? 16 : 0));
+    static constexpr int SLAB_BYTES = TG * PITCH;
     static __host__ __device__ constexpr int rec_bytes(int R) { return R * TG * REC; }
-    static __host__ __device__ constexpr int smem_bytes(int R) { return SLAB_BYTES + rec_bytes(R) + TG * 4 + 16; }
+    // slab tile, records, per-demo flags, work counter + 2 retry-list counters, 2 retry lists of NT entries
+    static __host__ __device__ constexpr int main_bytes(int R) {
+        return ((rec_bytes(R) > SLAB_BYTES ? rec_bytes(R) : SLAB_BYTES) + 15) & ~15;
+    }
+    static __host__ __device__ constexpr int smem_bytes(int R) { return main_bytes(R) + TG * 4 + 16 + 2 * NT * 4; }
 };
 
 // "is this factor all zero" over packed token words: OR of (word ^ zero_pat) under the factor's byte mask
@@ -168,17 +176,18 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
 }
 
 template <int S, int NT, bool SAMPLE, int NTHR, bool GUARD>
-__global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
+__global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 6))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
                 long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags) {
     using C = DemoCfg<S, NT>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_slab = smem;
-    uint8_t *s_rec = smem + C::SLAB_BYTES;                                    // [R][TG][REC]
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_rec + C::rec_bytes(R)); // [TG]
-    uint32_t *s_work = s_flag + C::TG;
+    uint8_t *s_rec = smem;  // [TG][R][REC] accumulate records (phases A, B) ...
+    uint8_t *s_slab = smem; // ... then the slab tile [TG][PITCH] (end of B, C) in the same bytes
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + C::main_bytes(R)); // [TG]
+    uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
+    uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -187,60 +196,102 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
     const int npairs = ng * R;
 
     for (int g = tid; g < C::TG; g += NT) s_flag[g] = 0;
-    if (tid == 0) *s_work = 0;
+    if (tid < 3) s_work[tid] = 0;
     __syncthreads();
 
     if constexpr (SAMPLE) {
-        // ---------------- A. draw the factor triples of the tile.  A rejected triple just bumps the lane's try,
-        // an accepted one is stored and the lane takes the next pair -- lanes never wait for another lane's
-        // rejection loop; pairs are handed out with one atomic per warp and round.
-        int p = npairs, t = 0, g = 0, r = 0;
-        uint32_t d_lo = 0, d_hi = 0;
-        bool need = true;
-        while (true) {
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+        // ---------------- A. draw the factor triples of the tile.
+        // A1: every lane runs a (pair, try) state machine: a rejected triple just bumps the lane's try, an accepted
+        // one is stored and the lane takes the next fresh pair (one atomic per warp and round) -- all 32 lanes draw in
+        // every round.  When the fresh pairs run out the warp parks its pending retries in a shared list, and
+        // A2: the CTA works the retry lists off densely, 32 retries per warp-round, until none is left.
+        auto decode = [&](int p, int &g, int &r, uint32_t &d_lo, uint32_t &d_hi) {
+            g = magic_r ? (int)__umulhi((uint32_t)p, magic_r) : p; // p / R  (p * R < 2^32; magic 0 <=> R == 1)
+            r = p - g * R;
+            const unsigned long long d = first_demo + (unsigned long long)(g0 + g);
+            d_lo = (uint32_t)d, d_hi = (uint32_t)(d >> 32);
+        };
+        // one try of pair (g, r); returns true when the pair is finished (accepted or forced)
+        auto attempt = [&](int g, int r, uint32_t d_lo, uint32_t d_hi, int t) -> bool {
+            uint32_t words[G::TP / 4];
+#pragma unroll
+            for (int w = C::NW; w < G::TP / 4; w++) words[w] = 0;
+            bool ok = draw_triple<S, NTHR>(words, d_lo, d_hi, r, t, cat);
+            if (!ok && t + 1 >= max_tries) { // bounded retries: forced unit triple (the reference would loop forever, Q11)
+#pragma unroll
+                for (int w = 0; w < C::NW; w++) words[w] = 0;
+#pragma unroll
+                for (int q = 0; q < 3 * S; q++)
+                    words[q >> 2] |= (((q % S) == 0 ? cat.top_tok : (uint32_t)shift) & 0xFFu) << (8 * (q & 3));
+                atomicOr(&s_flag[g], (uint32_t)TG_FLAG_EXHAUSTED);
+                ok = true;
+            }
+            if (ok) {
+                uint4 *dst = reinterpret_cast<uint4 *>(tape + (size_t)r * tape_step_stride + (g0 + g) * G::TP);
+#pragma unroll
+                for (int w = 0; w < G::TP / 16; w++)
+                    dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
+                emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+            }
+            return ok;
+        };
+        // park (pair | try << 16) of the lanes with `pending` in retry list `which`
+        auto park = [&](bool pending, int p, int t, int which) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
             if (m) {
                 const int leader = __ffs(m) - 1;
                 int base = 0;
-                if (lane == leader) base = (int)atomicAdd(s_work, (uint32_t)__popc(m));
+                if (lane == leader) base = (int)atomicAdd(&s_work[1 + which], (uint32_t)__popc(m));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (need) {
-                    p = base + __popc(m & ((1u << lane) - 1u));
-                    t = 0, need = false;
-                    if (p < npairs) {
-                        g = magic_r ? (int)__umulhi((uint32_t)p, magic_r) : p; // p / R  (p * R < 2^32; magic 0 <=> R == 1)
-                        r = p - g * R;
-                        const unsigned long long d = first_demo + (unsigned long long)(g0 + g);
-                        d_lo = (uint32_t)d, d_hi = (uint32_t)(d >> 32);
+                if (pending) s_list[which * NT + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)p | ((uint32_t)t << 16);
+            }
+        };
+        {
+            int p = npairs, t = 0, g = 0, r = 0;
+            uint32_t d_lo = 0, d_hi = 0;
+            bool need = true;
+            while (true) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = (int)atomicAdd(&s_work[0], (uint32_t)__popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (need) {
+                        p = base + __popc(m & ((1u << lane) - 1u));
+                        t = 0, need = false;
+                        if (p < npairs) decode(p, g, r, d_lo, d_hi);
                     }
                 }
-            }
-            if (__ballot_sync(0xFFFFFFFFu, p < npairs) == 0) break;
-            if (p < npairs) {
-                uint32_t words[G::TP / 4];
-#pragma unroll
-                for (int w = C::NW; w < G::TP / 4; w++) words[w] = 0;
-                bool ok = draw_triple<S, NTHR>(words, d_lo, d_hi, r, t, cat);
-                if (!ok && t + 1 >= max_tries) { // bounded retries: forced unit triple (the reference would loop forever, Q11)
-#pragma unroll
-                    for (int w = 0; w < C::NW; w++) words[w] = 0;
-#pragma unroll
-                    for (int q = 0; q < 3 * S; q++)
-                        words[q >> 2] |= (((q % S) == 0 ? cat.top_tok : (uint32_t)shift) & 0xFFu) << (8 * (q & 3));
-                    atomicOr(&s_flag[g], (uint32_t)TG_FLAG_EXHAUSTED);
-                    ok = true;
+                if (__ballot_sync(0xFFFFFFFFu, p >= npairs) != 0) { // fresh pairs ran out for this warp
+                    park(p < npairs, p, t, 0);
+                    break;
                 }
-                if (ok) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(tape + (size_t)r * tape_step_stride + (g0 + g) * G::TP);
-#pragma unroll
-                    for (int w = 0; w < G::TP / 16; w++)
-                        dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
-                    emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)r * C::TG + g) * C::REC));
+                if (attempt(g, r, d_lo, d_hi, t))
                     need = true;
-                } else {
+                else
                     t++;
-                }
             }
+        }
+        __syncthreads();
+        for (int cur = 0;; cur ^= 1) {
+            const int n = (int)s_work[1 + cur];
+            if (n == 0) break;
+            __syncthreads(); // everybody has read the size of list cur before anybody refills the other one
+            if (tid == 0) s_work[1 + (cur ^ 1)] = 0;
+            __syncthreads();
+            const bool have = tid < n;
+            int p = 0, t = 0, g = 0, r = 0;
+            uint32_t d_lo = 0, d_hi = 0;
+            bool pending = false;
+            if (have) {
+                const uint32_t it = s_list[cur * NT + tid];
+                p = (int)(it & 0xFFFFu), t = (int)(it >> 16);
+                decode(p, g, r, d_lo, d_hi);
+                pending = !attempt(g, r, d_lo, d_hi, t);
+            }
+            park(pending, p, t + 1, cur ^ 1);
+            __syncthreads();
         }
     } else {
         // ---------------- A'. replay: build the records from the tape in HBM
@@ -254,7 +305,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
                 const uint4 q = src[w];
                 words[4 * w] = q.x, words[4 * w + 1] = q.y, words[4 * w + 2] = q.z, words[4 * w + 3] = q.w;
             }
-            emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)r * C::TG + g) * C::REC));
+            emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
         }
     }
     __syncthreads();
@@ -263,18 +314,20 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
     constexpr int KW = C::KW;
     const int g = tid / S, j = tid % S;
     constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu; // valid bytes of the last word
-    if (tid < C::ACTIVE && g < ng) {
-        int32_t acc[S][KW];
+    const bool worker = tid < C::ACTIVE && g < ng;
+    int32_t acc[S][KW];
 #pragma unroll
-        for (int i = 0; i < S; i++)
+    for (int i = 0; i < S; i++)
 #pragma unroll
-            for (int m = 0; m < KW; m++) acc[i][m] = 0;
+        for (int m = 0; m < KW; m++) acc[i][m] = 0;
+    uint32_t bad = 0;
+    if (worker) {
         int bound = 0;
-        const uint8_t *rec0 = s_rec + (size_t)g * C::REC;
+        const uint8_t *rec0 = s_rec + (size_t)g * R * C::REC;
         const int voff = 4 * KW + S + j; // byte offset of v_j in the record
 #pragma unroll 2
         for (int r = 0; r < R; r++) {
-            const uint8_t *rec = rec0 + (size_t)r * (C::TG * C::REC);
+            const uint8_t *rec = rec0 + (size_t)r * C::REC;
             uint32_t q[C::REC / 4];
 #pragma unroll
             for (int m = 0; m < C::REC / 16; m++) {
@@ -299,63 +352,82 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : 3)
                 for (int m = 0; m < KW; m++) acc[i][m] += ui * vw[m];
             }
         }
-        uint32_t bad = 0;
-        uint8_t *gbase = s_slab + (size_t)g * G::GP + j * S;
         if (GUARD && bound * shift * shift > 191) {
             // a final entry might alias inside the packed words: recompute this thread's entries one by one
-#pragma unroll 1
-            for (int i = 0; i < S; i++)
-#pragma unroll 1
-                for (int k = 0; k < S; k++) {
-                    int e = 0;
-                    for (int r = 0; r < R; r++) {
-                        const uint8_t *rec = rec0 + (size_t)r * (C::TG * C::REC);
-                        const int8_t *cb = reinterpret_cast<const int8_t *>(rec) + 4 * KW;
-                        const uint32_t wb = (reinterpret_cast<const uint32_t *>(rec)[k >> 2] + H4) ^ H4; // integer form -> bytes
-                        e += (int)cb[i] * (int)cb[S + j] * (int)(int8_t)((wb >> (8 * (k & 3))) & 0xFFu);
-                    }
-                    if (e < -64 || e > 63) bad = 1;
-                    gbase[i * G::RP + k] = (uint8_t)e;
-                }
-        } else {
-            // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k
 #pragma unroll
-            for (int i = 0; i < S; i++) {
+            for (int i = 0; i < S; i++)
 #pragma unroll
                 for (int m = 0; m < KW; m++) {
-                    const uint32_t t = ((uint32_t)acc[i][m] + H4) ^ H4;
-                    bad |= (t ^ (t << 1)) & ((m == KW - 1) ? (WLAST & H4) : H4);
-                    if constexpr (S % 4 == 0) {
-                        reinterpret_cast<uint32_t *>(gbase + i * G::RP)[m] = t;
-                    } else {
-#pragma unroll
-                        for (int k = 4 * m; k < S && k < 4 * m + 4; k++) gbase[i * G::RP + k] = (uint8_t)(t >> (8 * (k & 3)));
+                    uint32_t word = 0;
+#pragma unroll 1
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int k = 4 * m + kk;
+                        if (k >= S) break;
+                        int e = 0;
+#pragma unroll 1
+                        for (int r = 0; r < R; r++) {
+                            const uint8_t *rec = rec0 + (size_t)r * C::REC;
+                            const int8_t *cb = reinterpret_cast<const int8_t *>(rec) + 4 * KW;
+                            const uint32_t wb = (reinterpret_cast<const uint32_t *>(rec)[m] + H4) ^ H4; // integer form -> bytes
+                            e += (int)cb[i] * (int)cb[S + j] * (int)(int8_t)((wb >> (8 * kk)) & 0xFFu);
+                        }
+                        if (e < -64 || e > 63) bad = 1;
+                        word |= ((uint32_t)e & 0xFFu) << (8 * kk);
                     }
+                    acc[i][m] = (int32_t)word;
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < S; i++)
+#pragma unroll
+                for (int m = 0; m < KW; m++) {
+                    const uint32_t t = ((uint32_t)acc[i][m] + H4) ^ H4; // integer form -> two's complement bytes
+                    bad |= (t ^ (t << 1)) & ((m == KW - 1) ? (WLAST & H4) : H4);
+                    acc[i][m] = (int32_t)t;
+                }
+        }
+    }
+    __syncthreads(); // every record has been consumed: the slab tile takes over the same shared memory
+    if (worker) {
+        // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k; the last j also zeroes the row padding,
+        // j = 0 the game padding
+        uint8_t *gbase = s_slab + (size_t)g * C::PITCH + j * S;
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+#pragma unroll
+            for (int m = 0; m < KW; m++) {
+                const uint32_t t = (uint32_t)acc[i][m];
+                if constexpr (S % 4 == 0) {
+                    reinterpret_cast<uint32_t *>(gbase + i * G::RP)[m] = t;
+                } else {
+#pragma unroll
+                    for (int k = 4 * m; k < S && k < 4 * m + 4; k++) gbase[i * G::RP + k] = (uint8_t)(t >> (8 * (k & 3)));
                 }
             }
+            if constexpr (G::RP != G::S2) {
+                if (j == S - 1)
+#pragma unroll
+                    for (int x = S; x < S + G::RP - G::S2; x++) gbase[i * G::RP + x] = 0;
+            }
+        }
+        if constexpr (G::GP != S * G::RP) {
+            if (j == 0)
+#pragma unroll
+                for (int x = S * G::RP; x < G::GP; x += 4) *reinterpret_cast<uint32_t *>(gbase + x) = 0u;
         }
         if (bad) atomicOr(&s_flag[g], (uint32_t)TG_FLAG_RANGE);
-    }
-    // row / game padding of the tile is zero (slab contract)
-    if constexpr (G::RP != G::S2 || G::GP != S * G::RP) {
-        constexpr int PADR = G::RP - G::S2, PADG = G::GP - S * G::RP;
-        for (int e = tid; e < ng * (S * PADR + PADG); e += NT) {
-            const int gg = e / (S * PADR + PADG), x = e % (S * PADR + PADG);
-            const int off = x < S * PADR ? (x / (PADR ? PADR : 1)) * G::RP + G::S2 + x % (PADR ? PADR : 1) : S * G::RP + (x - S * PADR);
-            s_slab[(size_t)gg * G::GP + off] = 0;
-        }
     }
     fence_proxy_async();
     __syncthreads();
 
-    // ---------------- C. tile out
-    if (tid == 0) {
-        bulk_s2g(slab + g0 * G::GP, s_slab, (uint32_t)(ng * G::GP));
+    // ---------------- C. tile out: one bulk store per game (row / game padding of the tile was zeroed up front)
+    if (tid < ng) {
+        bulk_s2g(slab + (g0 + tid) * G::GP, s_slab + (size_t)tid * C::PITCH, (uint32_t)G::GP);
         bulk_commit();
     }
     if (flags)
         for (int gg = tid; gg < ng; gg += NT) flags[g0 + gg] = (uint8_t)s_flag[gg];
-    if (tid == 0) bulk_wait<0>();
+    if (tid < ng) bulk_wait<0>();
 }
 
 template <int S, int NT, bool SAMPLE, int NTHR>
