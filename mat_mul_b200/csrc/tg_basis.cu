@@ -8,8 +8,21 @@
 // with A, B, C integer and unimodular.  Parity is pinned by our own int64
 // oracle (oracle/tg_oracle.c orc_change_of_basis) and algebraic invariants.
 //
-// One CTA per game.  The three mode products are done as three passes of the
-// SAME routine "contract the slowest axis, write the result rotated":
+// Fast path (basis_fast_kernel): a group of S*W threads per game, several games
+// per CTA, three passes through shared memory:
+//   C. Y[a][b][k'] = sum_k C[k'][k] T[a][b][k]   -- the contracted axis is the packed
+//      one: DP4A over 4 consecutive k, exact int32 results, their maximum tracked;
+//   A. Z[i][b][.]  = sum_a A[i][a] Y[a][b][.]    -- one IMAD per LPW entries: the
+//   B. T'[i][j][.] = sum_b B[j][b] Z[i][b][.]       k' axis is packed LPW entries per
+//      word (3 x 10 bit for S = 9, 2 x 16 bit otherwise) in integer form
+//      sum_l y_l 2^(LB l), linear in the scalar matrix entry.
+// The packed passes are exact while every entry fits its lane; that is
+// guaranteed up front by  max|Y| * ||A||_inf * ||B||_inf <= 2^(LB-1) - 1.  A game
+// that fails the test (large matrices) is marked and redone by the exact int32
+// kernel below -- results are identical either way.
+//
+// Exact path (basis_kernel): one CTA per game, three passes of the SAME routine
+// "contract the slowest axis, write the result rotated":
 //     X[b][c][i] = sum_a A[i][a] T[a][b][c]
 //     Y[c][i][j] = sum_b B[j][b] X[b][c][i]
 //     Z[i][j][k] = sum_c C[k][c] Y[c][i][j]
@@ -48,10 +61,13 @@ __device__ __forceinline__ void mode_pass(const int32_t *__restrict__ in, int32_
     }
 }
 
+constexpr uint8_t BASIS_REDO = 0x80; // internal: set by the fast kernel, cleared by the exact one
+
+// only_marked: visit every game, redo those the fast kernel marked with BASIS_REDO
 template <int S>
 __global__ void __launch_bounds__(BasisCfg<S>::NT)
     basis_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
-                 int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
+                 int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N, int only_marked) {
     using C = BasisCfg<S>;
     using G = Geo<S>;
     constexpr int NT = C::NT;
@@ -63,8 +79,24 @@ __global__ void __launch_bounds__(BasisCfg<S>::NT)
     uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_m + 3 * C::S2);
 
     const int tid = threadIdx.x;
-    const long long n = blockIdx.x;
-    if (n >= N) return;
+    // all games (grid-stride), or only the marked ones of this CTA's contiguous chunk of the flags array
+    __shared__ int s_list[1024];
+    __shared__ int s_cnt;
+    const long long chunk = only_marked ? (N + gridDim.x - 1) / gridDim.x : 0;
+    const long long lo = only_marked ? chunk * blockIdx.x : blockIdx.x, hi = only_marked ? min(N, lo + chunk) : N;
+    for (long long base = lo; base < hi; base += only_marked ? 1024 : (long long)gridDim.x) {
+    int cnt = 1;
+    if (only_marked) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (long long q = base + tid; q < min(hi, base + 1024); q += NT)
+            if (flags[q] & BASIS_REDO) s_list[atomicAdd(&s_cnt, 1)] = (int)(q - base);
+        __syncthreads();
+        cnt = s_cnt;
+    }
+    for (int it = 0; it < cnt; it++) {
+    const long long n = only_marked ? base + s_list[it] : base;
+    __syncthreads();
     const uint32_t *src = reinterpret_cast<const uint32_t *>(slab_in + n * G::GP);
     for (int w = tid; w < G::GP / 4; w += NT) reinterpret_cast<uint32_t *>(s_in)[w] = src[w];
     const int8_t *m = mats + n * mat_stride;
@@ -103,6 +135,216 @@ __global__ void __launch_bounds__(BasisCfg<S>::NT)
     if (bad) atomicOr(s_flag, bad);
     __syncthreads();
     if (tid == 0 && flags) flags[n] = (uint8_t)*s_flag;
+    }
+    }
+}
+
+// ------------------------------------------------------------------ fast path
+template <int S>
+struct BasisFast {
+    using G = Geo<S>;
+    static constexpr int LPW = (S == 9) ? 3 : 2;        // entries per packed word
+    static constexpr int LB = (S == 9) ? 10 : 16;       // bits per lane
+    static constexpr int LMAX = (1 << (LB - 1)) - 1;    // every entry must stay in [-LMAX, LMAX]
+    static constexpr int W = (S + LPW - 1) / LPW;       // packed words per run of S entries
+    static constexpr int TPG = S * W;                   // threads per game
+    static constexpr int BG = S / W;                    // runs per thread in pass C
+    static constexpr int KW4 = (S + 3) / 4;             // byte words per run (DP4A operands)
+    static constexpr int GPC = S == 9 ? 8 : (S == 16 ? 2 : 32); // games per CTA
+    static constexpr int NT = GPC * TPG;                // 216 / 256 / 256
+    static constexpr int PITCH = G::GP + (S == 9 ? 32 : (S == 4 ? 16 : 0)); // tile pitch (bank spread)
+    static constexpr int YW = S * S * W;                // words of Y (and of Z)
+    static constexpr int RW = (S + 3) & ~3;             // int32 per (padded) matrix row: rows are read as int4
+    static constexpr int YB = (YW * 4 + 15) & ~15;
+    // per game, every part 16-byte aligned: tile, A and B as int32 [S][RW], C as packed bytes [S][4 words],
+    // {max|Y|, normA, normB, flag}, Y, Z
+    static constexpr int GAME_BYTES = PITCH + 2 * S * RW * 4 + S * 16 + 16 + 2 * YB;
+    static constexpr int SMEM_BYTES = GPC * GAME_BYTES + 16;
+    static_assert(KW4 <= 4 && GAME_BYTES % 16 == 0, "layout");
+    static_assert(S % W == 0, "runs do not split evenly over the threads of a game");
+};
+
+template <int S>
+__global__ void __launch_bounds__(BasisFast<S>::NT)
+    basis_fast_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
+                      int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
+    using F = BasisFast<S>;
+    using G = Geo<S>;
+    constexpr int W = F::W, LPW = F::LPW, LB = F::LB, KW4 = F::KW4, S2 = S * S;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);
+    const int tid = threadIdx.x;
+    const int gl = tid / F::TPG, t = tid % F::TPG; // game slot, thread within the game
+    const long long g0 = (long long)blockIdx.x * F::GPC;
+    const int ng = (int)min((long long)F::GPC, N - g0);
+    uint8_t *gbase = smem + 16 + (size_t)gl * F::GAME_BYTES;
+    uint8_t *s_tile = gbase;
+    constexpr int RW = F::RW;
+    int32_t *s_ma = reinterpret_cast<int32_t *>(gbase + F::PITCH);
+    int32_t *s_mb = s_ma + S * RW;
+    uint32_t *s_cp = reinterpret_cast<uint32_t *>(s_mb + S * RW);
+    int32_t *s_st = reinterpret_cast<int32_t *>(s_cp + S * 4); // {max|Y|, normA, normB, bad}
+    int32_t *s_y = s_st + 4;
+    int32_t *s_z = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(s_y) + F::YB);
+    const bool live = gl < ng;
+
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(s_bar, (uint32_t)(ng * G::GP));
+        for (int g = 0; g < ng; g++)
+            bulk_g2s(smem + 16 + (size_t)g * F::GAME_BYTES, slab_in + (g0 + g) * G::GP, (uint32_t)G::GP, s_bar);
+    }
+    if (live) {
+        const int8_t *m = mats + (g0 + gl) * mat_stride;
+        if (t < 4) s_st[t] = 0;
+        for (int q = t; q < S * RW; q += F::TPG) {
+            const int r = q / RW, a = q % RW;
+            s_ma[q] = a < S ? (int32_t)m[r * S + a] : 0;
+            s_mb[q] = a < S ? (int32_t)m[S2 + r * S + a] : 0;
+        }
+        for (int q = t; q < S * 4; q += F::TPG) { // C[k'][4m .. 4m+3] as bytes, zero beyond S
+            const int kp = q / 4, mw = q % 4;
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (4 * mw + b < S) word |= ((uint32_t)(uint8_t)m[2 * S2 + kp * S + 4 * mw + b]) << (8 * b);
+            s_cp[q] = word;
+        }
+    }
+    __syncthreads();
+    if (live && t < 2 * S) { // row norms of A (t < S) and B
+        const int32_t *row = (t < S ? s_ma : s_mb) + (t % S) * RW;
+        int nrm = 0;
+#pragma unroll
+        for (int a = 0; a < S; a++) nrm += abs(row[a]);
+        atomicMax(&s_st[t < S ? 1 : 2], nrm);
+    }
+    mbar_wait(s_bar, 0);
+
+    // ---------------- pass C: Y[a][b][k'] = sum_k C[k'][k] T[a][b][k]  (DP4A), packed LPW per word
+    if (live) {
+        const int a = t / W, bg = t % W;
+        int mx = 0;
+        uint32_t x[F::BG][KW4];
+#pragma unroll
+        for (int bb = 0; bb < F::BG; bb++) {
+            const int off = a * G::RP + (bg * F::BG + bb) * S;
+            if constexpr (S % 4 == 0) {
+#pragma unroll
+                for (int mw = 0; mw < KW4; mw++) x[bb][mw] = *reinterpret_cast<const uint32_t *>(s_tile + off + 4 * mw);
+            } else {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_tile + (off & ~3));
+                const int sh = 8 * (off & 3);
+                uint32_t raw[KW4 + 1];
+#pragma unroll
+                for (int mw = 0; mw <= KW4; mw++) raw[mw] = wp[mw]; // stays inside the (padded) tile
+#pragma unroll
+                for (int mw = 0; mw < KW4; mw++) x[bb][mw] = __funnelshift_r(raw[mw], raw[mw + 1], sh);
+                x[bb][KW4 - 1] &= 0xFFFFFFFFu >> (8 * (4 - S % 4));
+            }
+        }
+        int y[F::BG][S];
+#pragma unroll
+        for (int kp = 0; kp < S; kp++) {
+            const uint4 c4 = reinterpret_cast<const uint4 *>(s_cp)[kp];
+            const uint32_t cw4[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int bb = 0; bb < F::BG; bb++) {
+                int acc = 0;
+#pragma unroll
+                for (int mw = 0; mw < KW4; mw++) acc = __dp4a((int)x[bb][mw], (int)cw4[mw], acc);
+                y[bb][kp] = acc;
+                mx = max(mx, abs(acc));
+            }
+        }
+#pragma unroll
+        for (int bb = 0; bb < F::BG; bb++)
+#pragma unroll
+            for (int cw = 0; cw < W; cw++) {
+                int word = 0;
+#pragma unroll
+                for (int l = LPW - 1; l >= 0; l--)
+                    if (cw * LPW + l < S) word = word * (1 << LB) + y[bb][cw * LPW + l];
+                s_y[(a * S + bg * F::BG + bb) * W + cw] = word;
+            }
+        atomicMax(&s_st[0], mx);
+    }
+    __syncthreads();
+    // packed passes are exact iff max|Y| * ||A|| <= LMAX and max|Y| * ||A|| * ||B|| <= LMAX
+    bool fast = false;
+    if (live) {
+        const long long za = (long long)s_st[0] * s_st[1];
+        fast = za <= F::LMAX && za * s_st[2] <= F::LMAX;
+    }
+    // ---------------- pass A: Z[i][b][cw] = sum_a A[i][a] Y[a][b][cw]
+    if (fast) {
+        int y[S];
+#pragma unroll
+        for (int a = 0; a < S; a++) y[a] = s_y[a * S * W + t];
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            int mrow[RW];
+#pragma unroll
+            for (int q = 0; q < RW / 4; q++) {
+                const int4 m4 = reinterpret_cast<const int4 *>(s_ma + i * RW)[q];
+                mrow[4 * q] = m4.x, mrow[4 * q + 1] = m4.y, mrow[4 * q + 2] = m4.z, mrow[4 * q + 3] = m4.w;
+            }
+            int acc = 0;
+#pragma unroll
+            for (int a = 0; a < S; a++) acc += mrow[a] * y[a];
+            s_z[i * S * W + t] = acc;
+        }
+    }
+    __syncthreads();
+    // ---------------- pass B: T'[i][j][cw] = sum_b B[j][b] Z[i][b][cw]; unpack, range test, bytes into the tile
+    if (fast) {
+        const int i = t / W, cw = t % W;
+        int z[S];
+#pragma unroll
+        for (int b = 0; b < S; b++) z[b] = s_z[(i * S + b) * W + cw];
+        constexpr uint32_t HALF = 1u << (LB - 1);
+        constexpr uint32_t BIAS = LPW == 3 ? (HALF | (HALF << LB) | (HALF << (2 * LB))) : (HALF | (HALF << LB));
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            int mrow[RW];
+#pragma unroll
+            for (int q = 0; q < RW / 4; q++) {
+                const int4 m4 = reinterpret_cast<const int4 *>(s_mb + j * RW)[q];
+                mrow[4 * q] = m4.x, mrow[4 * q + 1] = m4.y, mrow[4 * q + 2] = m4.z, mrow[4 * q + 3] = m4.w;
+            }
+            int acc = 0;
+#pragma unroll
+            for (int b = 0; b < S; b++) acc += mrow[b] * z[b];
+            const uint32_t u = (uint32_t)acc + BIAS;
+#pragma unroll
+            for (int l = 0; l < LPW; l++) {
+                const int kp = cw * LPW + l;
+                if (kp < S) {
+                    const int v = (int)((u >> (LB * l)) & ((1u << LB) - 1u)) - (int)HALF;
+                    bad |= (v < -64) | (v > 63);
+                    s_tile[i * G::RP + j * S + kp] = (uint8_t)v;
+                }
+            }
+        }
+        if (bad) s_st[3] = TG_FLAG_RANGE;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (live && t == 0) {
+        if (fast) {
+            bulk_s2g(slab_out + (g0 + gl) * G::GP, s_tile, (uint32_t)G::GP);
+            bulk_commit();
+            flags[g0 + gl] = (uint8_t)s_st[3];
+            bulk_wait<0>();
+        } else {
+            flags[g0 + gl] = BASIS_REDO;
+        }
+    }
 }
 
 // tokens of one game-step: coef' = M coef for the three factors; token' = coef' + shift_out
@@ -193,11 +435,26 @@ int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, 
     if (N > 0x7FFFFFFFLL) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long ms = per_game ? 3LL * S * S : 0;
+    // fast packed kernel first; it marks the games whose intermediates do not fit its lanes and the exact kernel
+    // redoes exactly those.  Without a flags array there is nowhere to leave the mark: exact kernel for all.
+    const int exact_grid = (int)(N < 148 * 8 ? N : 148 * 8);
+#define TG_BASIS_CASE(SS)                                                                                              \
+    case SS: {                                                                                                         \
+        using F = tg::BasisFast<SS>;                                                                                   \
+        if (flags) {                                                                                                   \
+            auto fast = tg::basis_fast_kernel<SS>;                                                                     \
+            TG_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));           \
+            fast<<<(unsigned)((N + F::GPC - 1) / F::GPC), F::NT, F::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out, flags, N); \
+        }                                                                                                              \
+        tg::basis_kernel<SS><<<flags ? exact_grid : (int)N, tg::BasisCfg<SS>::NT, tg::BasisCfg<SS>::SMEM_BYTES, st>>>(  \
+            slab_in, mats, ms, slab_out, flags, N, flags ? 1 : 0);                                                     \
+    } break;
     switch (S) {
-    case 4: tg::basis_kernel<4><<<(int)N, tg::BasisCfg<4>::NT, tg::BasisCfg<4>::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out, flags, N); break;
-    case 9: tg::basis_kernel<9><<<(int)N, tg::BasisCfg<9>::NT, tg::BasisCfg<9>::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out, flags, N); break;
-    case 16: tg::basis_kernel<16><<<(int)N, tg::BasisCfg<16>::NT, tg::BasisCfg<16>::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out, flags, N); break; // 39 KB smem
+        TG_BASIS_CASE(4)
+        TG_BASIS_CASE(9)
+        TG_BASIS_CASE(16)
     }
+#undef TG_BASIS_CASE
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }

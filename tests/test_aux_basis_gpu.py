@@ -133,3 +133,24 @@ def test_change_of_basis_shared_triple_and_identity(env):
     inv = torch.from_numpy(np.stack([P.T, np.eye(S, dtype=np.int64), np.eye(S, dtype=np.int64)]).astype(np.int8)).cuda()
     back, _ = env.change_of_basis(out, inv, S)
     assert torch.equal(back, slab)
+
+
+@pytest.mark.parametrize("S,amp,dens", [(4, 3, 1.0), (9, 3, 0.6), (9, 1, 0.2), (16, 2, 0.5), (16, 7, 1.0)])
+def test_change_of_basis_large_matrices_take_the_exact_path(env, S, amp, dens):
+    # dense / large matrices overflow the packed lanes of the fast kernel: those games are redone by the exact
+    # int32 kernel, and the result is the same int64 einsum either way
+    N = 97
+    rng = np.random.default_rng(S * 10 + amp)
+    T = rng.integers(-20, 21, (N, S, S, S)) * (rng.random((N, S, S, S)) < 0.3)
+    m = rng.integers(-amp, amp + 1, (N, 3, S, S)) * (rng.random((N, 3, S, S)) < dens)
+    m[::5] = np.eye(S, dtype=np.int64)  # some games stay on the fast path
+    slab = torch.from_numpy(dense_to_slab(T)).cuda()
+    out, flags = env.change_of_basis(slab, torch.from_numpy(m.astype(np.int8)).cuda(), S)
+    want = np.einsum("nia,njb,nkc,nabc->nijk", m[:, 0], m[:, 1], m[:, 2], T)
+    f = flags.cpu().numpy()
+    assert not (f & 0x80).any()
+    assert np.array_equal((f & 4) != 0, (np.abs(want.reshape(N, -1) + 0.5) > 64).any(1))
+    ok = np.abs(want.reshape(N, -1)).max(1) <= 127
+    assert ok.sum() >= N // 5
+    assert np.array_equal(slab_to_dense(out.cpu().numpy()[ok], S), want[ok])
+    assert np.array_equal(slab_to_dense(out.cpu().numpy(), S).astype(np.int8), want.astype(np.int8))  # low byte always
