@@ -146,23 +146,47 @@ struct BasisFast {
     static constexpr int LPW = (S == 9) ? 3 : 2;        // entries per packed word
     static constexpr int LB = (S == 9) ? 10 : 16;       // bits per lane
     static constexpr int LMAX = (1 << (LB - 1)) - 1;    // every entry must stay in [-LMAX, LMAX]
-    static constexpr int W = (S + LPW - 1) / LPW;       // packed words per run of S entries
-    static constexpr int TPG = S * W;                   // threads per game
-    static constexpr int BG = S / W;                    // runs per thread in pass C
+    static constexpr int W = (S + LPW - 1) / LPW;       // packed words per run of S entries: 3 / 8 / 2
+    static constexpr int CB = S == 9 ? 3 : (S == 16 ? 4 : 2); // words (columns) of a run owned by one thread
+    static constexpr int VEC = S == 4 ? 2 : 4;          // words per vector access of a thread's columns
+    static constexpr int NSPLIT = W / CB;               // threads sharing a run: 1 / 2 / 1
+    static constexpr int WP = NSPLIT * VEC;             // padded words per run: 4 / 8 / 2
+    static constexpr int TPG = S * NSPLIT;              // threads per game: 9 / 32 / 4
+    static constexpr int RPT = S / NSPLIT;              // runs per thread in pass C: 9 / 8 / 4
+    static constexpr int BB = S == 9 ? 3 : (S == 16 ? 2 : 4); // ... worked off BB at a time
     static constexpr int KW4 = (S + 3) / 4;             // byte words per run (DP4A operands)
-    static constexpr int GPC = S == 9 ? 8 : (S == 16 ? 2 : 32); // games per CTA
-    static constexpr int NT = GPC * TPG;                // 216 / 256 / 256
+    static constexpr int GPC = S == 9 ? 24 : (S == 16 ? 4 : 64); // games per CTA
+    static constexpr int NT = GPC * TPG;                // 216 / 128 / 256
     static constexpr int PITCH = G::GP + (S == 9 ? 32 : (S == 4 ? 16 : 0)); // tile pitch (bank spread)
-    static constexpr int YW = S * S * W;                // words of Y (and of Z)
     static constexpr int RW = (S + 3) & ~3;             // int32 per (padded) matrix row: rows are read as int4
-    static constexpr int YB = (YW * 4 + 15) & ~15;
-    // per game, every part 16-byte aligned: tile, A and B as int32 [S][RW], C as packed bytes [S][4 words],
-    // {max|Y|, normA, normB, flag}, Y, Z
-    static constexpr int GAME_BYTES = PITCH + 2 * S * RW * 4 + S * 16 + 16 + 2 * YB;
+    static constexpr int YB = S * S * WP * 4;           // bytes of Y (Z is written over it in place)
+    // per game, every part 16-byte aligned: tile, Y/Z, A and B as int32 [S][RW], C as packed bytes [S][4 words],
+    // {max|Y|, normA, normB, flag}
+    static constexpr int GAME_BYTES = PITCH + YB + 2 * S * RW * 4 + S * 16 + 16;
     static constexpr int SMEM_BYTES = GPC * GAME_BYTES + 16;
-    static_assert(KW4 <= 4 && GAME_BYTES % 16 == 0, "layout");
-    static_assert(S % W == 0, "runs do not split evenly over the threads of a game");
+    static_assert(W % CB == 0 && S % NSPLIT == 0 && RPT % BB == 0 && KW4 <= 4 && GAME_BYTES % 16 == 0, "layout");
 };
+
+template <int N>
+struct VecW;
+template <>
+struct VecW<2> { using T = int2; };
+template <>
+struct VecW<4> { using T = int4; };
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const int32_t *p, int out[VEC]) {
+    const typename VecW<VEC>::T v = *reinterpret_cast<const typename VecW<VEC>::T *>(p);
+    out[0] = v.x, out[1] = v.y;
+    if constexpr (VEC == 4) out[2] = v.z, out[3] = v.w;
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(int32_t *p, const int in[VEC]) {
+    typename VecW<VEC>::T v;
+    v.x = in[0], v.y = in[1];
+    if constexpr (VEC == 4) v.z = in[2], v.w = in[3];
+    *reinterpret_cast<typename VecW<VEC>::T *>(p) = v;
+}
 
 template <int S>
 __global__ void __launch_bounds__(BasisFast<S>::NT)
@@ -170,24 +194,26 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
                       int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
     using F = BasisFast<S>;
     using G = Geo<S>;
-    constexpr int W = F::W, LPW = F::LPW, LB = F::LB, KW4 = F::KW4, S2 = S * S;
+    constexpr int W = F::W, LPW = F::LPW, LB = F::LB, KW4 = F::KW4, S2 = S * S, RW = F::RW, CB = F::CB, VEC = F::VEC,
+                  WP = F::WP, BB = F::BB;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);
     const int tid = threadIdx.x;
     const int gl = tid / F::TPG, t = tid % F::TPG; // game slot, thread within the game
+    const int rr = t / F::NSPLIT, h = t % F::NSPLIT; // the row index this thread owns in a pass, its column split
     const long long g0 = (long long)blockIdx.x * F::GPC;
     const int ng = (int)min((long long)F::GPC, N - g0);
     uint8_t *gbase = smem + 16 + (size_t)gl * F::GAME_BYTES;
     uint8_t *s_tile = gbase;
-    constexpr int RW = F::RW;
-    int32_t *s_ma = reinterpret_cast<int32_t *>(gbase + F::PITCH);
+    int32_t *s_y = reinterpret_cast<int32_t *>(gbase + F::PITCH);
+    int32_t *s_ma = reinterpret_cast<int32_t *>(gbase + F::PITCH + F::YB);
     int32_t *s_mb = s_ma + S * RW;
     uint32_t *s_cp = reinterpret_cast<uint32_t *>(s_mb + S * RW);
     int32_t *s_st = reinterpret_cast<int32_t *>(s_cp + S * 4); // {max|Y|, normA, normB, bad}
-    int32_t *s_y = s_st + 4;
-    int32_t *s_z = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(s_y) + F::YB);
     const bool live = gl < ng;
 
+    int32_t *s_nrm = s_st + 1;
+    if (live && t < 4) s_st[t] = 0;
     if (tid == 0) {
         mbar_init(s_bar, 1);
         mbar_fence_init();
@@ -200,77 +226,86 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     }
     if (live) {
         const int8_t *m = mats + (g0 + gl) * mat_stride;
-        if (t < 4) s_st[t] = 0;
-        for (int q = t; q < S * RW; q += F::TPG) {
-            const int r = q / RW, a = q % RW;
-            s_ma[q] = a < S ? (int32_t)m[r * S + a] : 0;
-            s_mb[q] = a < S ? (int32_t)m[S2 + r * S + a] : 0;
-        }
-        for (int q = t; q < S * 4; q += F::TPG) { // C[k'][4m .. 4m+3] as bytes, zero beyond S
-            const int kp = q / 4, mw = q % 4;
-            uint32_t word = 0;
+        // one matrix row per thread and step: A and B rows -> int32 (padded to RW, read as int4 later) and their
+        // 1-norms, C rows -> bytes packed four to a word
+        for (int r = t; r < 3 * S; r += F::TPG) {
+            const int f = r / S, row = r % S;
+            int v[RW];
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (4 * mw + b < S) word |= ((uint32_t)(uint8_t)m[2 * S2 + kp * S + 4 * mw + b]) << (8 * b);
-            s_cp[q] = word;
+            for (int a = 0; a < RW; a++) v[a] = a < S ? (int)m[f * S2 + row * S + a] : 0;
+            if (f < 2) {
+                int nrm = 0;
+#pragma unroll
+                for (int a = 0; a < S; a++) nrm += abs(v[a]);
+#pragma unroll
+                for (int q = 0; q < RW / 4; q++) st_vec<4>((f == 0 ? s_ma : s_mb) + row * RW + 4 * q, v + 4 * q);
+                atomicMax(&s_nrm[f], nrm);
+            } else {
+                int words[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int a = 0; a < S; a++) words[a >> 2] |= (v[a] & 0xFF) << (8 * (a & 3));
+                st_vec<4>(reinterpret_cast<int32_t *>(s_cp) + row * 4, words);
+            }
         }
     }
     __syncthreads();
-    if (live && t < 2 * S) { // row norms of A (t < S) and B
-        const int32_t *row = (t < S ? s_ma : s_mb) + (t % S) * RW;
-        int nrm = 0;
-#pragma unroll
-        for (int a = 0; a < S; a++) nrm += abs(row[a]);
-        atomicMax(&s_st[t < S ? 1 : 2], nrm);
-    }
     mbar_wait(s_bar, 0);
 
-    // ---------------- pass C: Y[a][b][k'] = sum_k C[k'][k] T[a][b][k]  (DP4A), packed LPW per word
+    // ---------------- pass C: Y[a][b][k'] = sum_k C[k'][k] T[a][b][k]  (DP4A), packed LPW per word.
+    // thread (a = rr, h) owns the runs b = h*RPT .. h*RPT + RPT-1, BB at a time (one load of a C row serves BB runs)
     if (live) {
-        const int a = t / W, bg = t % W;
         int mx = 0;
-        uint32_t x[F::BG][KW4];
+#pragma unroll 1
+        for (int b0 = h * F::RPT; b0 < (h + 1) * F::RPT; b0 += BB) {
+            uint32_t x[BB][KW4];
 #pragma unroll
-        for (int bb = 0; bb < F::BG; bb++) {
-            const int off = a * G::RP + (bg * F::BG + bb) * S;
-            if constexpr (S % 4 == 0) {
+            for (int bb = 0; bb < BB; bb++) {
+                const int off = rr * G::RP + (b0 + bb) * S;
+                if constexpr (S % 4 == 0) {
 #pragma unroll
-                for (int mw = 0; mw < KW4; mw++) x[bb][mw] = *reinterpret_cast<const uint32_t *>(s_tile + off + 4 * mw);
-            } else {
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_tile + (off & ~3));
-                const int sh = 8 * (off & 3);
-                uint32_t raw[KW4 + 1];
+                    for (int mw = 0; mw < KW4; mw++) x[bb][mw] = *reinterpret_cast<const uint32_t *>(s_tile + off + 4 * mw);
+                } else {
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_tile + (off & ~3));
+                    const int sh = 8 * (off & 3);
+                    uint32_t raw[KW4 + 1];
 #pragma unroll
-                for (int mw = 0; mw <= KW4; mw++) raw[mw] = wp[mw]; // stays inside the (padded) tile
+                    for (int mw = 0; mw <= KW4; mw++) raw[mw] = wp[mw]; // stays inside the (padded) tile
 #pragma unroll
-                for (int mw = 0; mw < KW4; mw++) x[bb][mw] = __funnelshift_r(raw[mw], raw[mw + 1], sh);
-                x[bb][KW4 - 1] &= 0xFFFFFFFFu >> (8 * (4 - S % 4));
+                    for (int mw = 0; mw < KW4; mw++) x[bb][mw] = __funnelshift_r(raw[mw], raw[mw + 1], sh);
+                    x[bb][KW4 - 1] &= 0xFFFFFFFFu >> (8 * (4 - S % 4));
+                }
+            }
+            int y[BB][S];
+#pragma unroll
+            for (int kp = 0; kp < S; kp++) {
+                const uint4 c4 = reinterpret_cast<const uint4 *>(s_cp)[kp];
+                const uint32_t cw4[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int bb = 0; bb < BB; bb++) {
+                    int acc = 0;
+#pragma unroll
+                    for (int mw = 0; mw < KW4; mw++) acc = __dp4a((int)x[bb][mw], (int)cw4[mw], acc);
+                    y[bb][kp] = acc;
+                    mx = max(mx, abs(acc));
+                }
+            }
+#pragma unroll
+            for (int bb = 0; bb < BB; bb++) {
+                int words[F::NSPLIT * VEC];
+#pragma unroll
+                for (int q = 0; q < F::NSPLIT * VEC; q++) words[q] = 0;
+#pragma unroll
+                for (int cw = 0; cw < W; cw++) {
+                    int word = 0;
+#pragma unroll
+                    for (int l = LPW - 1; l >= 0; l--)
+                        if (cw * LPW + l < S) word = word * (1 << LB) + y[bb][cw * LPW + l];
+                    words[(cw / CB) * VEC + cw % CB] = word;
+                }
+#pragma unroll
+                for (int q = 0; q < F::NSPLIT; q++) st_vec<VEC>(s_y + (rr * S + b0 + bb) * WP + q * VEC, words + q * VEC);
             }
         }
-        int y[F::BG][S];
-#pragma unroll
-        for (int kp = 0; kp < S; kp++) {
-            const uint4 c4 = reinterpret_cast<const uint4 *>(s_cp)[kp];
-            const uint32_t cw4[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-            for (int bb = 0; bb < F::BG; bb++) {
-                int acc = 0;
-#pragma unroll
-                for (int mw = 0; mw < KW4; mw++) acc = __dp4a((int)x[bb][mw], (int)cw4[mw], acc);
-                y[bb][kp] = acc;
-                mx = max(mx, abs(acc));
-            }
-        }
-#pragma unroll
-        for (int bb = 0; bb < F::BG; bb++)
-#pragma unroll
-            for (int cw = 0; cw < W; cw++) {
-                int word = 0;
-#pragma unroll
-                for (int l = LPW - 1; l >= 0; l--)
-                    if (cw * LPW + l < S) word = word * (1 << LB) + y[bb][cw * LPW + l];
-                s_y[(a * S + bg * F::BG + bb) * W + cw] = word;
-            }
         atomicMax(&s_st[0], mx);
     }
     __syncthreads();
@@ -280,58 +315,67 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
         const long long za = (long long)s_st[0] * s_st[1];
         fast = za <= F::LMAX && za * s_st[2] <= F::LMAX;
     }
-    // ---------------- pass A: Z[i][b][cw] = sum_a A[i][a] Y[a][b][cw]
+    // ---------------- pass A: Z[i][b][.] = sum_a A[i][a] Y[a][b][.], thread (b = rr, h) works on its CB columns of
+    // every row, in place
     if (fast) {
-        int y[S];
+        int y[S][VEC];
 #pragma unroll
-        for (int a = 0; a < S; a++) y[a] = s_y[a * S * W + t];
+        for (int a = 0; a < S; a++) ld_vec<VEC>(s_y + (a * S + rr) * WP + h * VEC, y[a]);
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int mrow[RW];
 #pragma unroll
-            for (int q = 0; q < RW / 4; q++) {
-                const int4 m4 = reinterpret_cast<const int4 *>(s_ma + i * RW)[q];
-                mrow[4 * q] = m4.x, mrow[4 * q + 1] = m4.y, mrow[4 * q + 2] = m4.z, mrow[4 * q + 3] = m4.w;
-            }
-            int acc = 0;
+            for (int q = 0; q < RW / 4; q++) ld_vec<4>(s_ma + i * RW + 4 * q, mrow + 4 * q);
+            int acc[VEC];
 #pragma unroll
-            for (int a = 0; a < S; a++) acc += mrow[a] * y[a];
-            s_z[i * S * W + t] = acc;
+            for (int c = 0; c < VEC; c++) acc[c] = 0;
+#pragma unroll
+            for (int a = 0; a < S; a++)
+#pragma unroll
+                for (int c = 0; c < CB; c++) acc[c] += mrow[a] * y[a][c];
+            st_vec<VEC>(s_y + (i * S + rr) * WP + h * VEC, acc);
         }
     }
     __syncthreads();
-    // ---------------- pass B: T'[i][j][cw] = sum_b B[j][b] Z[i][b][cw]; unpack, range test, bytes into the tile
+    // ---------------- pass B: T'[i][j][.] = sum_b B[j][b] Z[i][b][.], thread (i = rr, h); range test on the packed
+    // words, low bytes of the lanes into the tile
     if (fast) {
-        const int i = t / W, cw = t % W;
-        int z[S];
+        int z[S][VEC];
 #pragma unroll
-        for (int b = 0; b < S; b++) z[b] = s_z[(i * S + b) * W + cw];
+        for (int b = 0; b < S; b++) ld_vec<VEC>(s_y + (rr * S + b) * WP + h * VEC, z[b]);
         constexpr uint32_t HALF = 1u << (LB - 1);
-        constexpr uint32_t BIAS = LPW == 3 ? (HALF | (HALF << LB) | (HALF << (2 * LB))) : (HALF | (HALF << LB));
-        bool bad = false;
+        constexpr uint32_t ONE = LPW == 3 ? (1u | (1u << LB) | (1u << (2 * LB))) : (1u | (1u << LB));
+        constexpr uint32_t LMASK = (1u << LB) - 1u;
+        uint32_t over = 0;
 #pragma unroll
         for (int j = 0; j < S; j++) {
             int mrow[RW];
 #pragma unroll
-            for (int q = 0; q < RW / 4; q++) {
-                const int4 m4 = reinterpret_cast<const int4 *>(s_mb + j * RW)[q];
-                mrow[4 * q] = m4.x, mrow[4 * q + 1] = m4.y, mrow[4 * q + 2] = m4.z, mrow[4 * q + 3] = m4.w;
+            for (int q = 0; q < RW / 4; q++) ld_vec<4>(s_mb + j * RW + 4 * q, mrow + 4 * q);
+            uint32_t u[CB];
+#pragma unroll
+            for (int c = 0; c < CB; c++) {
+                int acc = 0;
+#pragma unroll
+                for (int b = 0; b < S; b++) acc += mrow[b] * z[b][c];
+                u[c] = (uint32_t)acc + HALF * ONE; // lanes biased to [0, 2^LB)
+                // every lane in [HALF-64, HALF+63]  <=>  (lane - (HALF-64)) < 128 in every lane
+                over |= (u[c] - (HALF - 64u) * ONE) & ((LMASK & ~127u) * ONE);
             }
-            int acc = 0;
+            uint8_t *dst = s_tile + rr * G::RP + j * S + h * CB * LPW;
+            if constexpr (S == 9) {
 #pragma unroll
-            for (int b = 0; b < S; b++) acc += mrow[b] * z[b];
-            const uint32_t u = (uint32_t)acc + BIAS;
+                for (int c = 0; c < CB; c++)
 #pragma unroll
-            for (int l = 0; l < LPW; l++) {
-                const int kp = cw * LPW + l;
-                if (kp < S) {
-                    const int v = (int)((u >> (LB * l)) & ((1u << LB) - 1u)) - (int)HALF;
-                    bad |= (v < -64) | (v > 63);
-                    s_tile[i * G::RP + j * S + kp] = (uint8_t)v;
-                }
+                    for (int l = 0; l < LPW; l++) dst[c * LPW + l] = (uint8_t)(u[c] >> (LB * l)); // HALF = 0 mod 256
+            } else {
+                // 16-bit lanes: bytes 0 and 2 of each word are the int8 entries
+#pragma unroll
+                for (int c = 0; c < CB; c += 2)
+                    *reinterpret_cast<uint32_t *>(dst + 2 * c) = __byte_perm(u[c], u[c + 1], 0x6420);
             }
         }
-        if (bad) s_st[3] = TG_FLAG_RANGE;
+        if (over) s_st[3] = TG_FLAG_RANGE;
     }
     fence_proxy_async();
     __syncthreads();
@@ -437,7 +481,7 @@ int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, 
     const long long ms = per_game ? 3LL * S * S : 0;
     // fast packed kernel first; it marks the games whose intermediates do not fit its lanes and the exact kernel
     // redoes exactly those.  Without a flags array there is nowhere to leave the mark: exact kernel for all.
-    const int exact_grid = (int)(N < 148 * 8 ? N : 148 * 8);
+    const int exact_grid = (int)(N < 148 * 32 ? N : 148 * 32);
 #define TG_BASIS_CASE(SS)                                                                                              \
     case SS: {                                                                                                         \
         using F = tg::BasisFast<SS>;                                                                                   \
