@@ -122,7 +122,7 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, bar
     algo = S ** 3 + R * 3 * S
     out["demo_gen"] = {"metric": "synthetic_demos_per_sec", "value": B / ms * 1e3, "ms": ms, "R": R,
                        "algorithmic_bytes_per_demo": algo, "hbm_frac": B * algo / (ms * 1e-3) / 1e9 / peak,
-                       "bound": "issue (Philox draws + rank-1 accumulation), see DESIGN.md"}
+                       "bound": "issue slots (Philox draws + packed rank-1 accumulation on the INT pipes), see DESIGN.md 4"}
     ms = _time_ms(lambda: env.accumulate_demos(tape3, S, shift, slab=s2), 3, torch)
     out["demo_accumulate"] = {"value": B / ms * 1e3, "unit": "demos/s", "ms": ms}
     rev = tape3.flip(0).contiguous()
@@ -172,7 +172,7 @@ def cpu_reference_leg(S: int, shift: int, seconds: float = 12.0):
     t0 = time.perf_counter()
     orc.step_batch_f32(T, tok, shift, out, flags, nnz)
     one = time.perf_counter() - t0
-    reps = max(1, min(400, int(seconds / max(one, 1e-6))))
+    reps = max(1, min(20000, int(seconds / max(one, 1e-6))))
     return cores, Bs, reps, T, tok, out, flags, nnz
 
 
