@@ -157,12 +157,16 @@ struct BasisFast {
     static constexpr int KW4 = (S + 3) / 4;             // byte words per run (DP4A operands)
     static constexpr int GPC = S == 9 ? 24 : (S == 16 ? 4 : 64); // games per CTA
     static constexpr int NT = GPC * TPG;                // 216 / 128 / 256
-    static constexpr int PITCH = G::GP + (S == 9 ? 32 : (S == 4 ? 16 : 0)); // tile pitch (bank spread)
     static constexpr int RW = (S + 3) & ~3;             // int32 per (padded) matrix row: rows are read as int4
-    static constexpr int YB = S * S * WP * 4;           // bytes of Y (Z is written over it in place)
+    static constexpr int YROW = S * WP + (S == 16 ? 8 : 0); // words between Y[a][.][.] and Y[a+1][.][.], padded so that
+                                                        // lanes that differ in the first index hit different banks
+    static constexpr int YB = S * YROW * 4;             // bytes of Y (Z is written over it in place)
+    static constexpr int OROW = G::RP + (S == 16 ? 16 : 0); // row pitch of the OUTPUT tile (same reason); a padded
+                                                        // tile leaves row by row
+    static constexpr int TILE_BYTES = (((S * OROW > G::GP ? S * OROW : G::GP) + (S == 9 ? 32 : (S == 4 ? 16 : 0))) + 15) & ~15;
     // per game, every part 16-byte aligned: tile, Y/Z, A and B as int32 [S][RW], C as packed bytes [S][4 words],
     // {max|Y|, normA, normB, flag}
-    static constexpr int GAME_BYTES = PITCH + YB + 2 * S * RW * 4 + S * 16 + 16;
+    static constexpr int GAME_BYTES = TILE_BYTES + YB + 2 * S * RW * 4 + S * 16 + 16;
     static constexpr int SMEM_BYTES = GPC * GAME_BYTES + 16;
     static_assert(W % CB == 0 && S % NSPLIT == 0 && RPT % BB == 0 && KW4 <= 4 && GAME_BYTES % 16 == 0, "layout");
 };
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     using F = BasisFast<S>;
     using G = Geo<S>;
     constexpr int W = F::W, LPW = F::LPW, LB = F::LB, KW4 = F::KW4, S2 = S * S, RW = F::RW, CB = F::CB, VEC = F::VEC,
-                  WP = F::WP, BB = F::BB;
+                  WP = F::WP, BB = F::BB, YROW = F::YROW, OROW = F::OROW;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);
     const int tid = threadIdx.x;
@@ -205,8 +209,8 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     const int ng = (int)min((long long)F::GPC, N - g0);
     uint8_t *gbase = smem + 16 + (size_t)gl * F::GAME_BYTES;
     uint8_t *s_tile = gbase;
-    int32_t *s_y = reinterpret_cast<int32_t *>(gbase + F::PITCH);
-    int32_t *s_ma = reinterpret_cast<int32_t *>(gbase + F::PITCH + F::YB);
+    int32_t *s_y = reinterpret_cast<int32_t *>(gbase + F::TILE_BYTES);
+    int32_t *s_ma = reinterpret_cast<int32_t *>(gbase + F::TILE_BYTES + F::YB);
     int32_t *s_mb = s_ma + S * RW;
     uint32_t *s_cp = reinterpret_cast<uint32_t *>(s_mb + S * RW);
     int32_t *s_st = reinterpret_cast<int32_t *>(s_cp + S * 4); // {max|Y|, normA, normB, bad}
@@ -252,15 +256,17 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     mbar_wait(s_bar, 0);
 
     // ---------------- pass C: Y[a][b][k'] = sum_k C[k'][k] T[a][b][k]  (DP4A), packed LPW per word.
-    // thread (a = rr, h) owns the runs b = h*RPT .. h*RPT + RPT-1, BB at a time (one load of a C row serves BB runs)
+    // thread (b = t % S, t / S) owns the runs (a, b), a = (t/S)*RPT .. +RPT-1, BB at a time (one load of a C row
+    // serves BB runs); lanes differ in b, i.e. read neighbouring runs of the tile
     if (live) {
         int mx = 0;
+        const int bfix = t % S;
 #pragma unroll 1
-        for (int b0 = h * F::RPT; b0 < (h + 1) * F::RPT; b0 += BB) {
+        for (int a0 = (t / S) * F::RPT; a0 < (t / S + 1) * F::RPT; a0 += BB) {
             uint32_t x[BB][KW4];
 #pragma unroll
             for (int bb = 0; bb < BB; bb++) {
-                const int off = rr * G::RP + (b0 + bb) * S;
+                const int off = (a0 + bb) * G::RP + bfix * S;
                 if constexpr (S % 4 == 0) {
 #pragma unroll
                     for (int mw = 0; mw < KW4; mw++) x[bb][mw] = *reinterpret_cast<const uint32_t *>(s_tile + off + 4 * mw);
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
                     words[(cw / CB) * VEC + cw % CB] = word;
                 }
 #pragma unroll
-                for (int q = 0; q < F::NSPLIT; q++) st_vec<VEC>(s_y + (rr * S + b0 + bb) * WP + q * VEC, words + q * VEC);
+                for (int q = 0; q < F::NSPLIT; q++) st_vec<VEC>(s_y + (a0 + bb) * YROW + bfix * WP + q * VEC, words + q * VEC);
             }
         }
         atomicMax(&s_st[0], mx);
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     if (fast) {
         int y[S][VEC];
 #pragma unroll
-        for (int a = 0; a < S; a++) ld_vec<VEC>(s_y + (a * S + rr) * WP + h * VEC, y[a]);
+        for (int a = 0; a < S; a++) ld_vec<VEC>(s_y + a * YROW + rr * WP + h * VEC, y[a]);
 #pragma unroll
         for (int i = 0; i < S; i++) {
             int mrow[RW];
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
             for (int a = 0; a < S; a++)
 #pragma unroll
                 for (int c = 0; c < CB; c++) acc[c] += mrow[a] * y[a][c];
-            st_vec<VEC>(s_y + (i * S + rr) * WP + h * VEC, acc);
+            st_vec<VEC>(s_y + i * YROW + rr * WP + h * VEC, acc);
         }
     }
     __syncthreads();
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     if (fast) {
         int z[S][VEC];
 #pragma unroll
-        for (int b = 0; b < S; b++) ld_vec<VEC>(s_y + (rr * S + b) * WP + h * VEC, z[b]);
+        for (int b = 0; b < S; b++) ld_vec<VEC>(s_y + rr * YROW + b * WP + h * VEC, z[b]);
         constexpr uint32_t HALF = 1u << (LB - 1);
         constexpr uint32_t ONE = LPW == 3 ? (1u | (1u << LB) | (1u << (2 * LB))) : (1u | (1u << LB));
         constexpr uint32_t LMASK = (1u << LB) - 1u;
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
                 // every lane in [HALF-64, HALF+63]  <=>  (lane - (HALF-64)) < 128 in every lane
                 over |= (u[c] - (HALF - 64u) * ONE) & ((LMASK & ~127u) * ONE);
             }
-            uint8_t *dst = s_tile + rr * G::RP + j * S + h * CB * LPW;
+            uint8_t *dst = s_tile + rr * OROW + j * S + h * CB * LPW;
             if constexpr (S == 9) {
 #pragma unroll
                 for (int c = 0; c < CB; c++)
@@ -379,16 +385,20 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     }
     fence_proxy_async();
     __syncthreads();
-    if (live && t == 0) {
-        if (fast) {
+    if constexpr (OROW == G::RP) {
+        if (live && t == 0 && fast) {
             bulk_s2g(slab_out + (g0 + gl) * G::GP, s_tile, (uint32_t)G::GP);
             bulk_commit();
-            flags[g0 + gl] = (uint8_t)s_st[3];
             bulk_wait<0>();
-        } else {
-            flags[g0 + gl] = BASIS_REDO;
+        }
+    } else { // padded output tile: one bulk store per row
+        if (live && t < S && fast) {
+            bulk_s2g(slab_out + (g0 + gl) * G::GP + t * G::RP, s_tile + t * OROW, (uint32_t)G::RP);
+            bulk_commit();
+            bulk_wait<0>();
         }
     }
+    if (live && t == 0) flags[g0 + gl] = fast ? (uint8_t)s_st[3] : BASIS_REDO;
 }
 
 // tokens of one game-step: coef' = M coef for the three factors; token' = coef' + shift_out
