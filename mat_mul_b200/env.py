@@ -295,6 +295,22 @@ def demos_from_seed(n_demos: int, max_actions: int, S: int, values=(-1, 0, 1), p
     return tape, slab, flags, consumed
 
 
+def accumulate_demos_tc(tape: torch.Tensor, shift: int, slab: torch.Tensor | None = None):
+    """accumulate_demos for S = 16, R <= 64 on the tensor cores (tg_demo_accumulate_tc, experimental: tcgen05.mma
+    kind::i8, accumulators in TMEM).  Entries beyond int8 are stored saturated.  Returns (slab, flags)."""
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(16)
+    R, N = tape.shape[0], tape.shape[1]
+    if tape.shape[2] != lay.token_pitch:
+        raise TensorGameError(f"tape must be (R, N, {lay.token_pitch})")
+    if slab is None:
+        slab = torch.empty((N, lay.game_pitch), dtype=torch.int8, device=tape.device)
+    flags = torch.empty(N, dtype=torch.uint8, device=tape.device)
+    check(_lib.lib().tg_demo_accumulate_tc(_p(tape), N * lay.token_pitch, N, R, 16, shift, _p(slab), _p(flags), _stream()),
+          "tg_demo_accumulate_tc")
+    return slab, flags
+
+
 # ---------------------------------------------------------------- K4 / K6 / K7
 def demo_samples(tape: torch.Tensor, slab: torch.Tensor, idx: torch.Tensor, S: int, dim_t: int, replay_shift: int = 1):
     """Batch of SyntheticDemoDataset.__getitem__ results (datasets.py:77-122) from the in-HBM demo store.
