@@ -227,6 +227,7 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = env.bind_host_to_gpu(local)  # pinned staging buffers of the e2e leg land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -313,7 +314,8 @@ def main() -> None:
         e2e = {"value": world * Be * Ke / float(te.item()), "unit": "steps/s",
                "h2d_bytes_per_step": Be * (lay.game_pitch + lay.token_pitch),
                "d2h_bytes_per_step": Be * (lay.game_pitch + 5), "steps": Ke,
-               "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks over 3 streams)"}
+               "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks over 3 streams)",
+               "host_cores_bound": len(numa_cores)}
         del h_slab, h_tape, h_out
 
     # ---- episode statistics: the only collective of the path (two tiny all_reduces), outside the timed region

@@ -388,6 +388,28 @@ def change_of_basis(slab: torch.Tensor, mats: torch.Tensor, S: int, tape: torch.
     return out, tape_out, flags
 
 
+def bind_host_to_gpu(device: int = 0) -> list[int]:
+    """Pin the calling process to the CPU cores that are local to GPU `device` (NVML cpu affinity), so that the
+    pinned host buffers it allocates next are first-touched on that GPU's NUMA node.  Matters for the host-buffer
+    entry points (tg_step_host) when several ranks share one box.  Returns the cores (empty if unavailable)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cores = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return []
+
+
 class HostStepper:
     """End-to-end step for callers whose data lives in host memory (pinned
     numpy/torch CPU buffers): chunked H2D -> tg_step -> D2H over three streams
