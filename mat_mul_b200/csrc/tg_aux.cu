@@ -25,8 +25,11 @@ __device__ __forceinline__ void vw_bytes(const uint8_t *tok, const Lane<S> &L, i
     }
 }
 
-template <int S>
-__global__ void demo_sample_kernel(const uint8_t *__restrict__ tape, long long tape_step_stride,
+// PACK16: the head is accumulated two entries per 32-bit word (16-bit lanes in integer form, one IMAD per two
+// entries, half the registers -> more samples in flight); the host takes this path when R * cmax^3 + 128 fits int16.
+template <int S, bool PACK16>
+__global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
+    demo_sample_kernel(const uint8_t *__restrict__ tape, long long tape_step_stride,
                                    const int8_t *__restrict__ slab, long long N, int R, int dim_t, int replay_shift,
                                    const long long *__restrict__ idx, long long nb, float *__restrict__ states,
                                    float *__restrict__ scalars, long long *__restrict__ actions,
@@ -43,29 +46,60 @@ __global__ void demo_sample_kernel(const uint8_t *__restrict__ tape, long long t
     if (demo < 0 || demo >= N) return;
     const uint8_t *tk = tape + demo * G::TP;
     // head
-    int acc[S][4];
+    float *st = states + b * (long long)dim_t * G::S3;
     const int8_t *tg = slab + demo * G::GP + 4 * L.c;
-#pragma unroll
-    for (int i = 0; i < S; i++)
-#pragma unroll
-        for (int q = 0; q < 4; q++) acc[i][q] = (int)tg[i * G::RP + q];
-    for (int j = a + 1; j < R; j++) {
-        const uint8_t *tok = tk + (size_t)j * tape_step_stride;
-        int vw[4];
-        vw_bytes<S>(tok, L, replay_shift, vw);
+    if constexpr (PACK16) {
+        int acc[S][2];
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            const int u = (int)tok[i] - replay_shift;
-#pragma unroll
-            for (int q = 0; q < 4; q++) acc[i][q] -= u * vw[q];
+            const uint32_t t = *reinterpret_cast<const uint32_t *>(tg + i * G::RP);
+            acc[i][0] = (int)(int8_t)(t & 0xFFu) + ((int)(int8_t)((t >> 8) & 0xFFu)) * 65536;
+            acc[i][1] = (int)(int8_t)((t >> 16) & 0xFFu) + ((int)(int8_t)(t >> 24)) * 65536;
         }
+        for (int j = a + 1; j < R; j++) {
+            const uint8_t *tok = tk + (size_t)j * tape_step_stride;
+            int vw[4];
+            vw_bytes<S>(tok, L, replay_shift, vw);
+            const int p0 = vw[0] + vw[1] * 65536, p1 = vw[2] + vw[3] * 65536;
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const int u = (int)tok[i] - replay_shift;
+                acc[i][0] -= u * p0;
+                acc[i][1] -= u * p1;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < S; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int x = acc[i][q >> 1];
+                const int lo = (int)(short)(x & 0xFFFF);
+                const int v = (q & 1) ? (x - lo) >> 16 : lo;
+                if (4 * L.c + q < G::S2) st[i * G::S2 + 4 * L.c + q] = (float)v;
+            }
+    } else {
+        int acc[S][4];
+#pragma unroll
+        for (int i = 0; i < S; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[i][q] = (int)tg[i * G::RP + q];
+        for (int j = a + 1; j < R; j++) {
+            const uint8_t *tok = tk + (size_t)j * tape_step_stride;
+            int vw[4];
+            vw_bytes<S>(tok, L, replay_shift, vw);
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const int u = (int)tok[i] - replay_shift;
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[i][q] -= u * vw[q];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < S; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (4 * L.c + q < G::S2) st[i * G::S2 + 4 * L.c + q] = (float)acc[i][q];
     }
-    float *st = states + b * (long long)dim_t * G::S3;
-#pragma unroll
-    for (int i = 0; i < S; i++)
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (4 * L.c + q < G::S2) st[i * G::S2 + 4 * L.c + q] = (float)acc[i][q];
     // history slots: rank-1 tensors of the next actions, latest first
     const int hi = min(a + dim_t, R);
     for (int s = 1; s < dim_t; s++) {
@@ -212,11 +246,20 @@ int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *
     if (nb == 0) return TG_OK;
     if (!tape || !slab || !idx || !states || !scalars || !actions || !rewards) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    // tokens are <= 2 * 4 (tape contract), so |coefficient| <= cmax; the 16-bit packed head is exact while
+    // 127 + R * cmax^3 fits an int16 lane
+    const long long cmax = replay_shift > 8 - replay_shift ? replay_shift : 8 - replay_shift;
+    const bool pack16 = replay_shift >= 0 && replay_shift <= 8 && 127 + (long long)R * cmax * cmax * cmax <= 32767;
     TG_SWITCH_S(S, {
         const long long threads = nb * tg::Geo<kS>::WR;
-        tg::demo_sample_kernel<kS><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-            tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb, states, scalars,
-            (long long *)actions, rewards);
+        if (pack16)
+            tg::demo_sample_kernel<kS, true><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb, states, scalars,
+                (long long *)actions, rewards);
+        else
+            tg::demo_sample_kernel<kS, false><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb, states, scalars,
+                (long long *)actions, rewards);
     });
     TG_CUDA(cudaGetLastError());
     return TG_OK;
