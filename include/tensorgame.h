@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TG_VERSION 100
+#define TG_VERSION 101
 
 #define TG_OK 0
 #define TG_E_ARG (-1)     /* bad argument (unsupported S, null pointer, misaligned buffer) */
@@ -107,8 +107,9 @@ int tg_replay(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stri
  *
  * Throughput mode (device RNG; contract in DESIGN.md, restated by the oracle):
  * demo d = first_demo + n draws its R factor triples from Philox4x32-10 keyed
- * by (seed, d), 16-bit draws against the CDF of `probs` over `values` (HOST
- * arrays, n_values <= 8, values in [-shift, shift]); a triple is rejected iff
+ * by seed with counter (d_lo, d_hi, term | try << 16, block): 15-bit draws
+ * against floor(cdf * 2^15) of `probs` over `values` (HOST arrays,
+ * n_values <= 8, values in [-shift, shift], max_tries <= 65535); a triple is rejected iff
  * u, v or w is all zero (utils.py:229), at most max_tries tries per term
  * (TG_FLAG_EXHAUSTED).  Writes tokens (values + shift) to the tape, the summed
  * target tensors to slab [N][GP] and TG_FLAG_RANGE/EXHAUSTED to flags (may be
