@@ -134,9 +134,13 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, bar
     nb = min(B, 1 << 18)
     mats = env.sample_unimodular(nb, S, seed=3, p_nonzero={4: 0.3, 9: 0.08, 16: 0.03}[S], device=dev)
     ms = _time_ms(lambda: env.change_of_basis(slab[:nb], mats, S), 3, torch)
-    algo = S ** 3 + 3 * S * S + S ** 3
+    algo = S ** 3 + 3 * S * S + S ** 3        # what this implementation moves: int8 in, three int8 matrices, int8 out
+    algo_survey = S ** 3 + 3 * S * S + 2 * S ** 3  # int8 in, int16 out
     out["change_of_basis"] = {"value": nb / ms * 1e3, "unit": "games/s", "ms": ms, "games": nb,
-                              "hbm_frac": nb * algo / (ms * 1e-3) / 1e9 / peak, "int_ops_per_game": 6 * S ** 4}
+                              "hbm_frac": nb * algo / (ms * 1e-3) / 1e9 / peak,
+                              "hbm_frac_survey_bytes": nb * algo_survey / (ms * 1e-3) / 1e9 / peak,
+                              "algorithmic_bytes_per_game": algo, "survey_bytes_per_game": algo_survey,
+                              "int_ops_per_game": 6 * S ** 4}
     idx = torch.randint(0, B * R, (1 << 16,), device=dev)
     ms = _time_ms(lambda: env.demo_samples(tape3, slab, idx, S, 2, replay_shift=shift), 3, torch)
     out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2,

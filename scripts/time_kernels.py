@@ -36,7 +36,8 @@ for S, R, N, vals, probs, shift, p in [(4, 7, 1 << 22, (-1, 0, 1), (0.15, 0.7, 0
     nb = min(N, 1 << 18)
     mats = env.sample_unimodular(nb, S, seed=3, p_nonzero=p)
     ms = t_ms(lambda: env.change_of_basis(slab[:nb], mats, S))
-    print(f"S={S} change_of_basis: {ms:.3f} ms {nb / ms / 1e6:.4f} G games/s hbm_frac={(nb * (3 * S**3 + 3 * S * S)) / ms / 1e6 / 6549.1:.3f}")
+    print(f"S={S} change_of_basis: {ms:.3f} ms {nb / ms / 1e6:.4f} G games/s hbm_frac={(nb * (2 * S**3 + 3 * S * S)) / ms / 1e6 / 6549.1:.3f} "
+          f"(int8 out; {(nb * (3 * S**3 + 3 * S * S)) / ms / 1e6 / 6549.1:.3f} on SURVEY 8(d)'s int16-out bytes)")
     idx = torch.randint(0, N * R, (1 << 16,), device="cuda")
     ms = t_ms(lambda: env.demo_samples(tape, slab, idx, S, 2, replay_shift=shift))
     print(f"S={S} demo_sample T=2: {ms:.3f} ms {idx.numel() / ms / 1e6:.4f} G samples/s")
