@@ -145,6 +145,19 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, bar
     ms = _time_ms(lambda: env.demo_samples(tape3, slab, idx, S, 2, replay_shift=shift), 3, torch)
     out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2,
                           "hbm_frac": idx.numel() * (2 * S ** 3 * 4) / (ms * 1e-3) / 1e9 / peak}
+    if S == 9:
+        # BASELINE.json quotes the metric at 4x4x4 too: the same two numbers on 2^22 games of the 2x2 matmul size
+        # (reference defaults: coefficients {-1,0,1}, P(0) = 0.7, R = 7, shift = 1)
+        S4, R4, B4 = 4, 7, 1 << 22
+        t4, s4, _ = env.make_synthetic_demos(B4, R4, S4, (-1, 0, 1), (0.15, 0.7, 0.15), 1, seed=2, device=dev)
+        ms = _time_ms(lambda: env.make_synthetic_demos(B4, R4, S4, (-1, 0, 1), (0.15, 0.7, 0.15), 1, seed=2, device=dev, tape=t4, slab=s4), 3, torch)
+        algo4 = S4 ** 3 + R4 * 3 * S4
+        o4, f4, n4 = torch.empty_like(s4), torch.empty(B4, dtype=torch.uint8, device=dev), torch.empty(B4, dtype=torch.int32, device=dev)
+        ms_step = _time_ms(lambda: env.step_batch(s4, t4[R4 - 1], S4, 1, out=o4, flags=f4, nnz=n4), 10, torch)
+        out["size_4x4x4"] = {"games": B4, "synthetic_demos_per_sec": B4 / ms * 1e3, "demo_hbm_frac": B4 * algo4 / (ms * 1e-3) / 1e9 / peak,
+                             "env_steps_per_sec": B4 / ms_step * 1e3,
+                             "step_hbm_frac": B4 * ALGO_BYTES[4] / (ms_step * 1e-3) / 1e9 / peak}
+        del t4, s4, o4
     if world > 1:  # demo all-gather timed as its own phase (NVLink-bound)
         from mat_mul_b200 import dist as tgd
 
