@@ -64,11 +64,13 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
-template <int S, int NT>
+template <int S, int NT, int NPASS = 1>
 struct DemoCfg {
     using G = Geo<S>;
-    static constexpr int TG = NT / S;      // demos per CTA; S threads per demo in phase B (thread = factor index j)
-    static constexpr int ACTIVE = TG * S;
+    static constexpr int GPASS = NT / S;        // demos per pass of phase B: S threads per demo (thread = factor index j)
+    static constexpr int TG = GPASS * NPASS;    // demos per CTA: a bigger tile amortises the tail of the sampling phase
+    static constexpr int ACTIVE = GPASS * S;
+    static constexpr bool OVERLAY = NPASS == 1; // the slab tile reuses the bytes of the accumulate records
     static constexpr int KW = (S + 3) / 4;       // packed words per run of S entries (one (i, j), k = 0..S-1)
     static constexpr int NCW = (2 * S + 3) / 4;  // words holding the u and v coefficient bytes
     static constexpr int NW = (3 * S + 3) / 4;   // token words of one action
@@ -81,8 +83,9 @@ struct DemoCfg {
     static constexpr int SLAB_BYTES = TG * PITCH;
     static __host__ __device__ constexpr int rec_bytes(int R) { return R * TG * REC; }
     // slab tile, records, per-demo flags, work counter + 2 retry-list counters, 2 retry lists of NT entries
+    static __host__ __device__ constexpr int rec_region(int R) { return (rec_bytes(R) + 15) & ~15; }
     static __host__ __device__ constexpr int main_bytes(int R) {
-        return ((rec_bytes(R) > SLAB_BYTES ? rec_bytes(R) : SLAB_BYTES) + 15) & ~15;
+        return OVERLAY ? (((rec_bytes(R) > SLAB_BYTES ? rec_bytes(R) : SLAB_BYTES) + 15) & ~15) : rec_region(R) + SLAB_BYTES;
     }
     static __host__ __device__ constexpr int smem_bytes(int R) { return main_bytes(R) + TG * 4 + 16 + 2 * NT * 4; }
 };
@@ -175,16 +178,17 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
     return (int)prmt(w, 0u, sel);
 }
 
-template <int S, int NT, bool SAMPLE, int NTHR, bool GUARD>
-__global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 6))
+template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD>
+__global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 4))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
                 long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags) {
-    using C = DemoCfg<S, NT>;
+    using C = DemoCfg<S, NT, NPASS>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_rec = smem;  // [TG][R][REC] accumulate records (phases A, B) ...
-    uint8_t *s_slab = smem; // ... then the slab tile [TG][PITCH] (end of B, C) in the same bytes
+    // ... then (OVERLAY) the slab tile [TG][PITCH] (end of B, C) in the same bytes, else a region of its own
+    uint8_t *s_slab = C::OVERLAY ? smem : smem + C::rec_region(R);
     uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + C::main_bytes(R)); // [TG]
     uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
     uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16)
@@ -312,8 +316,11 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 6))
 
     // ---------------- B. accumulate the R rank-1 terms in registers
     constexpr int KW = C::KW;
-    const int g = tid / S, j = tid % S;
     constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu; // valid bytes of the last word
+    const int j = tid % S;
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; pass++) {
+    const int g = pass * C::GPASS + tid / S;
     const bool worker = tid < C::ACTIVE && g < ng;
     int32_t acc[S][KW];
 #pragma unroll
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 6))
                 }
         }
     }
-    __syncthreads(); // every record has been consumed: the slab tile takes over the same shared memory
+    if constexpr (C::OVERLAY) __syncthreads(); // every record has been consumed: the slab tile takes over the same bytes
     if (worker) {
         // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k; the last j also zeroes the row padding,
         // j = 0 the game padding
@@ -417,23 +424,22 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 6))
         }
         if (bad) atomicOr(&s_flag[g], (uint32_t)TG_FLAG_RANGE);
     }
+    } // pass
     fence_proxy_async();
     __syncthreads();
 
-    // ---------------- C. tile out: one bulk store per game (row / game padding of the tile was zeroed up front)
-    if (tid < ng) {
-        bulk_s2g(slab + (g0 + tid) * G::GP, s_slab + (size_t)tid * C::PITCH, (uint32_t)G::GP);
-        bulk_commit();
-    }
+    // ---------------- C. tile out: one bulk store per game
+    for (int gg = tid; gg < ng; gg += NT) bulk_s2g(slab + (g0 + gg) * G::GP, s_slab + (size_t)gg * C::PITCH, (uint32_t)G::GP);
+    if (tid < ng) bulk_commit();
     if (flags)
         for (int gg = tid; gg < ng; gg += NT) flags[g0 + gg] = (uint8_t)s_flag[gg];
     if (tid < ng) bulk_wait<0>();
 }
 
-template <int S, int NT, bool SAMPLE, int NTHR>
+template <int S, int NT, int NPASS, bool SAMPLE, int NTHR>
 static int launch_demo(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
                        uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
-    using C = DemoCfg<S, NT>;
+    using C = DemoCfg<S, NT, NPASS>;
     const int smem = C::smem_bytes(R);
     if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
     const bool guard = (long long)R * shift * shift * shift > 191;
@@ -441,11 +447,11 @@ static int launch_demo(unsigned long long first, long long N, int R, int shift, 
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
     if (guard) {
-        auto kern = demo_kernel<S, NT, SAMPLE, NTHR, true>;
+        auto kern = demo_kernel<S, NT, NPASS, SAMPLE, NTHR, true>;
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
     } else {
-        auto kern = demo_kernel<S, NT, SAMPLE, NTHR, false>;
+        auto kern = demo_kernel<S, NT, NPASS, SAMPLE, NTHR, false>;
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
     }
@@ -457,9 +463,12 @@ template <bool SAMPLE, int NTHR>
 static int dispatch_demo(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
                          int max_tries, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     switch (S) {
-    case 4: return launch_demo<4, 256, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    case 9: return launch_demo<9, 256, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    case 16: return launch_demo<16, 256, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    case 4: // big tiles (4 passes of phase B) amortise the retry tail of the sampler; long action lists fall back
+        if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
+            return launch_demo<4, 256, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        return launch_demo<4, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    case 9: return launch_demo<9, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    case 16: return launch_demo<16, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
     }
     return TG_E_ARG;
 }
