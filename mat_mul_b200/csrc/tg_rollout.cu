@@ -9,9 +9,11 @@
 // The residual never leaves the SM: thread (game, word column c) keeps its S
 // row words in REGISTERS (offset-binary, see tg_step.cuh) for all K steps, so a
 // step costs one pack(v w) and S IMADs per thread.  Only the tokens stream
-// from HBM (TP bytes per game-step) through a small TMA-fed shared-memory
-// ring.  "Is the game solved" is one shared-memory vote + one CTA barrier per
-// step.  HBM traffic per game: 2*GP + K*TP + 9 bytes.
+// from HBM (TP bytes per game-step) through a small shared-memory ring that a
+// dedicated producer warp keeps full with TMA bulk copies (full/empty
+// mbarriers).  "Is the game solved" is one shared-memory vote + one named
+// barrier of the compute warps per step.  HBM traffic per game: 2*GP + K*TP + 9
+// bytes.
 #include "tg_step.cuh"
 
 namespace tg {
@@ -22,11 +24,12 @@ struct RollCfg {
     static constexpr int TG = NT / G::WR;      // games per CTA (one word column per thread)
     static constexpr int ACTIVE = TG * G::WR;
     static constexpr int TOK_BYTES = TG * G::TP;
-    static constexpr int SMEM_BYTES = NST * TOK_BYTES + 3 * TG * 4 + 2 * TG * 4 + NST * 8;
+    static constexpr int SMEM_BYTES = NST * TOK_BYTES + 4 * TG * 4 + 2 * TG * 4 + 2 * NST * 8;
+    static_assert((NST & (NST - 1)) == 0, "ring depth must be a power of two");
 };
 
 template <int S, int NT, int NST>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT + 32)
     rollout_kernel(const int8_t *__restrict__ slab_in, const uint8_t *__restrict__ tape, long long tape_step_stride, int K,
                    int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, int32_t *__restrict__ nnz,
                    int32_t *__restrict__ steps, long long B, int shift, int chk, int freeze) {
@@ -34,33 +37,28 @@ __global__ void __launch_bounds__(NT)
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_tok = smem;                                                     // [NST][TG][TP]
-    uint32_t *s_any = reinterpret_cast<uint32_t *>(smem + NST * C::TOK_BYTES); // [3][TG] votes "still non-zero"
-    uint32_t *s_sum = s_any + 3 * C::TG;                                       // [TG] final partial sums
+    uint32_t *s_any = reinterpret_cast<uint32_t *>(smem + NST * C::TOK_BYTES); // [4][TG] votes "still non-zero"
+    uint32_t *s_sum = s_any + 4 * C::TG;                                       // [TG] final partial sums
     uint32_t *s_steps = s_sum + C::TG;                                         // [TG]
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_steps + C::TG);           // [NST]
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_steps + C::TG);          // [NST] tokens of a step have landed
+    uint64_t *s_empty = s_full + NST;                                          // [NST] ... have been consumed
 
     const int tid = threadIdx.x;
     const long long g0 = (long long)blockIdx.x * C::TG;
     const int ng = (int)min((long long)C::TG, B - g0);
+    const bool compute = tid < NT;
     const bool active = tid < C::ACTIVE && (tid / G::WR) < ng;
     const int g = tid / G::WR;
     Lane<S> L;
     L.init(tid < C::ACTIVE ? tid % G::WR : 0);
 
-    for (int i = tid; i < 3 * C::TG; i += NT) s_any[i] = 0;
-    for (int i = tid; i < C::TG; i += NT) s_sum[i] = 0, s_steps[i] = 0;
+    for (int i = tid; i < 4 * C::TG; i += NT + 32) s_any[i] = 0;
+    for (int i = tid; i < C::TG; i += NT + 32) s_sum[i] = 0, s_steps[i] = 0;
     if (tid == 0) {
-        for (int s = 0; s < NST; s++) mbar_init(&s_bar[s], 1);
+        for (int s = 0; s < NST; s++) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], NT / 32);
         mbar_fence_init();
     }
     __syncthreads();
-    auto load_tokens = [&](int t) {
-        const int s = t % NST;
-        mbar_expect_tx(&s_bar[s], (uint32_t)(ng * G::TP));
-        bulk_g2s(s_tok + s * C::TOK_BYTES, tape + (size_t)t * tape_step_stride + g0 * G::TP, (uint32_t)(ng * G::TP), &s_bar[s]);
-    };
-    if (tid == 0)
-        for (int t = 0; t < NST && t < K; t++) load_tokens(t);
 
     // residual rows of this thread's word column, offset-binary
     uint32_t row[S];
@@ -79,41 +77,56 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
         for (int i = 0; i < S; i++) row[i] = H4;
     }
-    // vote on the initial state (slot 2 is the "step -1" slot)
-    if (active && nzw) s_any[2 * C::TG + g] = 1;
+    // vote on the initial state (slot 3 is the "step -1" slot)
+    if (active && nzw) s_any[3 * C::TG + g] = 1;
     __syncthreads();
-    bool alive = active && (!freeze || s_any[2 * C::TG + g] != 0);
+    bool alive = active && (!freeze || s_any[3 * C::TG + g] != 0);
     int until = chk;
     int my_steps = 0;
 
-    for (int t = 0; t < K; t++) {
-        const int st = t % NST;
-        mbar_wait(&s_bar[st], (uint32_t)(t / NST) & 1u);
-        const int slot = t % 3;
-        if (tid < C::TG) s_any[((t + 1) % 3) * C::TG + tid] = 0; // last read before the previous barrier
-        if (alive) {
-            const uint8_t *tok = s_tok + st * C::TOK_BYTES + g * G::TP;
-            const int32_t vw = pack_vw<S>(tok, L, shift);
-            const uint4 ut = *reinterpret_cast<const uint4 *>(tok);
-            const uint32_t uw[4] = {ut.x, ut.y, ut.z, ut.w};
-            uint32_t any = 0;
-            const uint32_t nvw = (uint32_t)(-vw);
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                row[i] += (uint32_t)coef_u(uw, i, shift) * nvw;
-                any |= row[i] ^ H4;
+    if (!compute) {
+        // ---------------- producer warp: one lane streams the tokens of step t into ring stage t % NST
+        if (tid == NT) {
+            const uint8_t *src = tape + g0 * G::TP;
+            for (int t = 0; t < K; t++, src += tape_step_stride) {
+                const int st = t & (NST - 1);
+                if (t >= NST) mbar_wait(&s_empty[st], (uint32_t)(t / NST - 1) & 1u); // every compute warp has read it
+                mbar_expect_tx(&s_full[st], (uint32_t)(ng * G::TP));
+                bulk_g2s(s_tok + st * C::TOK_BYTES, src, (uint32_t)(ng * G::TP), &s_full[st]);
             }
-            if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
-                until = chk;
-#pragma unroll
-                for (int i = 0; i < S; i++) bad |= ~(row[i] ^ (row[i] << 1));
-            }
-            my_steps = t + 1;
-            if (any & vmask) s_any[slot * C::TG + g] = 1;
         }
-        __syncthreads();
-        if (alive && freeze) alive = s_any[slot * C::TG + g] != 0;
-        if (tid == 0 && t + NST < K) load_tokens(t + NST); // stage st was fully read before the barrier
+    } else {
+        const uint8_t *tok0 = s_tok + g * G::TP;
+        for (int t = 0; t < K; t++) {
+            const int st = t & (NST - 1);
+            mbar_wait(&s_full[st], (uint32_t)(t / NST) & 1u);
+            // slot (t+2)&3 was last read right after the barrier of step t-2: every warp is past the barrier of t-1
+            if (tid < C::TG) s_any[((t + 2) & 3) * C::TG + tid] = 0;
+            if (alive) {
+                const uint8_t *tok = tok0 + st * C::TOK_BYTES;
+                const int32_t vw = pack_vw<S>(tok, L, shift);
+                const uint4 ut = *reinterpret_cast<const uint4 *>(tok);
+                const uint32_t uw[4] = {ut.x, ut.y, ut.z, ut.w};
+                uint32_t any = 0;
+                const uint32_t nvw = (uint32_t)(-vw);
+#pragma unroll
+                for (int i = 0; i < S; i++) {
+                    row[i] += (uint32_t)coef_u(uw, i, shift) * nvw;
+                    any |= row[i] ^ H4;
+                }
+                if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
+                    until = chk;
+#pragma unroll
+                    for (int i = 0; i < S; i++) bad |= ~(row[i] ^ (row[i] << 1));
+                }
+                my_steps = t + 1;
+                if (any & vmask) s_any[(t & 3) * C::TG + g] = 1;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); // compute warps only
+            if (alive && freeze) alive = s_any[(t & 3) * C::TG + g] != 0;
+        }
     }
 
     // final state out, per-game nnz / flags / steps
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(NT)
         if (L.c == 0) s_steps[g] = (uint32_t)my_steps;
     }
     __syncthreads();
-    for (int q = tid; q < ng; q += NT) {
+    for (int q = tid; q < ng; q += NT + 32) {
         const uint32_t sum = s_sum[q];
         flags[g0 + q] = (uint8_t)(partial_flags(sum) & ~TG_FLAG_NULL);
         nnz[g0 + q] = (int32_t)(sum & 0xFFFFu);
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(NT)
     }
     if constexpr (G::GP > S * G::RP) { // keep the slab tail padding of out-of-place results zero
         if (slab_out != slab_in)
-            for (int q = tid; q < ng * ((G::GP - S * G::RP) / 4); q += NT) {
+            for (int q = tid; q < ng * ((G::GP - S * G::RP) / 4); q += NT + 32) {
                 const int gg = q / ((G::GP - S * G::RP) / 4), w = q % ((G::GP - S * G::RP) / 4);
                 reinterpret_cast<uint32_t *>(slab_out + (g0 + gg) * G::GP + S * G::RP)[w] = 0;
             }
@@ -154,7 +167,7 @@ static int launch_rollout(const int8_t *slab_in, const uint8_t *tape, long long 
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
     const int s3 = shift * shift * shift;
     const int chk = s3 >= 64 ? 1 : 64 / s3;
-    rollout_kernel<S, NT, NST><<<(int)grid, NT, C::SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B,
+    rollout_kernel<S, NT, NST><<<(int)grid, NT + 32, C::SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B,
                                                                      shift, chk, freeze);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
