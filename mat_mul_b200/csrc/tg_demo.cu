@@ -292,9 +292,18 @@ __global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 4))
                 const uint32_t it = s_list[cur * NT + tid];
                 p = (int)(it & 0xFFFFu), t = (int)(it >> 16);
                 decode(p, g, r, d_lo, d_hi);
-                pending = !attempt(g, r, d_lo, d_hi, t);
+                pending = true;
             }
-            park(pending, p, t + 1, cur ^ 1);
+            // up to three tries per round: the rounds (and their CTA barriers) shrink geometrically faster
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                if (pending) {
+                    pending = !attempt(g, r, d_lo, d_hi, t);
+                    t++;
+                }
+                if (__ballot_sync(0xFFFFFFFFu, pending) == 0) break;
+            }
+            park(pending, p, t, cur ^ 1);
             __syncthreads();
         }
     } else {
