@@ -11,7 +11,9 @@ V5, P5 = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05)
 
 
 def t_ms(fn, n=5):
-    fn(); torch.cuda.synchronize()
+    for _ in range(3):  # the first launches of a kernel carry module-load / allocator latency on the host side
+        fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
