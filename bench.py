@@ -97,7 +97,8 @@ class ClockSampler:
 
 
 def _time_ms(fn, iters: int, torch) -> float:
-    fn()
+    for _ in range(3):  # first launches carry host-side module-load latency
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
