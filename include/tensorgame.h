@@ -83,6 +83,16 @@ int tg_unpack_actions_i64(const uint8_t *tape, int64_t *actions, int64_t B, int 
 int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz,
             int64_t B, int S, int shift, void *stream);
 
+/* ---- K8: batched leaf expansion ------------------------------------------ */
+/* children[b][c] = parents[b] - u(x)v(x)w of tape[b][c] for c < k (tape uint8 [B][k][TP], children int8
+ * [B][k][GP], flags / nnz / keys [B][k]); each parent is read once.  flags as in tg_step (TERMINAL = the child's
+ * head is all zero, NULL = the action changed nothing, RANGE), keys = tg_state_key of the child (may be NULL).
+ * Replaces, for B states at once, act.py:266-275 (get_child_states) together with the per-child
+ * remove_null_actions (utils.py:191-194), tensor_factorized (utils.py:181-188, act.py:177) and state key
+ * (utils.py:164-169, act.py:185-195) that extend_tree applies to the children. */
+int tg_expand_children(const int8_t *parents, const uint8_t *tape, int k, int8_t *children, uint8_t *flags, int32_t *nnz,
+                       uint64_t *keys, int64_t B, int S, int shift, void *stream);
+
 /* ---- K2: fused K-step rollout --------------------------------------------- */
 /* Applies tape[0..K-1] (step-major uint8 [K][B_total][TP], byte stride
  * tape_step_stride between steps) to every game, freezing a game once its

@@ -37,15 +37,16 @@ def _head_key(state: torch.Tensor) -> int:
 
 def get_child_states(state: torch.Tensor, actions: torch.Tensor, vec_cardinality=5):
     """act.py:266-275: for each of the k sampled actions, new_head = head - action_to_tensor(action) (token shift
-    fixed at 1) and history = the previous slots shifted by one.  One tg_step launch over bs*k games; the returned
+    fixed at 1) and history = the previous slots shifted by one.  One tg_expand_children launch; the returned
     list also carries the kernel's per-child flags (ChildStates)."""
     bs, k = actions.shape[:2]
     S = state.shape[-1]
     dev = _device()
     head = _heads_to_slab(state[:, 0], S)                                   # (bs, GP)
-    slab = head.unsqueeze(1).expand(bs, k, head.shape[-1]).reshape(bs * k, -1).contiguous()
-    tape = _env.pack_actions(actions.reshape(bs * k, -1).to(dev).to(torch.int64).contiguous(), S)
-    out, flags, nnz = _env.step_batch(slab, tape, S, 1)
+    tape = _env.pack_actions(actions.reshape(bs * k, -1).to(dev).to(torch.int64).contiguous(), S).reshape(bs, k, -1)
+    # one launch: the k children of every state, their null / terminal flags, non-zero counts and state keys (K8)
+    out, flags, nnz, keys = _env.expand_children(head, tape, S, 1)
+    out = out.reshape(bs * k, -1)
     new_heads = _env.expand_states(out, S).reshape(bs, k, S, S, S).to(device=state.device, dtype=state.dtype)
     children = ChildStates(torch.cat([new_heads[:, i : i + 1], state[:, :-1]], dim=1) for i in range(k))
     f = flags.reshape(bs, k)
@@ -53,7 +54,7 @@ def get_child_states(state: torch.Tensor, actions: torch.Tensor, vec_cardinality
     children.null_flags = ((f & _env.FLAG_NULL) != 0).all(0).cpu()
     children.terminal = ((f & _env.FLAG_TERMINAL) != 0).all(0).cpu()
     children.nnz = nnz.reshape(bs, k).cpu()
-    children.keys = _env.state_keys(out, S).reshape(bs, k)[0].cpu()
+    children.keys = keys.reshape(bs, k)[0].cpu()
     return children
 
 

@@ -194,8 +194,8 @@ __global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__re
 
 // ------------------------------------------------------------------ K7
 // 64-bit state key replacing the string key of utils.py:164-169 (dict key of
-// the MCTS tree, act.py:37...210): sum over non-zero entries e of
-// splitmix64((e+1) << 32 | uint32(value)), e the dense index (i*S+j)*S+k.
+// the MCTS tree, act.py:37...210): a linear hash, sum over entries e of value * C_e,
+// C_e = splitmix64(e+1) | 1, e the dense index (i*S+j)*S+k.
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -203,28 +203,42 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     return z ^ (z >> 31);
 }
 
+// key(T) = sum_e T[e] * C_e (mod 2^64), C_e = splitmix64(e + 1) | 1: one 64-bit multiply-add per non-zero entry, the
+// constants in a shared-memory table built at kernel start; per-game sums through shared memory, one store per game.
 template <int S>
-__global__ void state_key_kernel(const int8_t *__restrict__ slab, unsigned long long *__restrict__ keys, long long B) {
+__global__ void __launch_bounds__(256) state_key_kernel(const int8_t *__restrict__ slab, unsigned long long *__restrict__ keys,
+                                                        long long B) {
     using G = Geo<S>;
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long g = t / G::WR;
-    if (g >= B) return;
-    const int c = (int)(t % G::WR);
-    unsigned long long h = 0;
-    const uint32_t *col = reinterpret_cast<const uint32_t *>(slab + g * G::GP) + c;
-#pragma unroll
-    for (int i = 0; i < S; i++) {
-        const uint32_t w = col[i * G::WR];
-        if (w == 0) continue;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int v = (int)(int8_t)((w >> (8 * q)) & 0xFFu);
-            const int jk = 4 * c + q;
-            if (v != 0 && jk < G::S2)
-                h += splitmix64(((unsigned long long)(uint32_t)(i * G::S2 + jk + 1) << 32) | (uint32_t)v);
-        }
+    constexpr int TG = 256 / G::WR; // games per pass of the CTA
+    __shared__ unsigned long long s_c[S * G::RP]; // C by slab offset (i, 4c+q); 0 in the row padding
+    __shared__ unsigned long long s_key[TG];
+    const int tid = threadIdx.x;
+    for (int x = tid; x < S * G::RP; x += 256) {
+        const int i = x / G::RP, jk = x % G::RP;
+        s_c[x] = jk < G::S2 ? (splitmix64((unsigned long long)(i * G::S2 + jk + 1)) | 1ull) : 0ull;
     }
-    if (h) atomicAdd(&keys[g], h);
+    const int gl = tid / G::WR, c = tid % G::WR;
+    for (long long g0 = (long long)blockIdx.x * TG; g0 < B; g0 += (long long)gridDim.x * TG) {
+        if (tid < TG) s_key[tid] = 0;
+        __syncthreads();
+        const long long g = g0 + gl;
+        if (gl < TG && g < B) {
+            unsigned long long h = 0;
+            const uint32_t *col = reinterpret_cast<const uint32_t *>(slab + g * G::GP) + c;
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const uint32_t w = col[i * G::WR];
+                if (w == 0) continue;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    h += (unsigned long long)(long long)(int8_t)((w >> (8 * q)) & 0xFFu) * s_c[i * G::RP + 4 * c + q];
+            }
+            if (h) atomicAdd(&s_key[gl], h);
+        }
+        __syncthreads();
+        if (tid < TG && g0 + tid < B) keys[g0 + tid] = s_key[tid];
+        __syncthreads();
+    }
 }
 
 } // namespace tg
@@ -285,10 +299,9 @@ int tg_state_key(const int8_t *slab, uint64_t *keys, int64_t B, int S, void *str
     if (B == 0) return TG_OK;
     if (!slab || !keys) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    TG_CUDA(cudaMemsetAsync(keys, 0, (size_t)B * 8, st));
     TG_SWITCH_S(S, {
-        const long long threads = B * tg::Geo<kS>::WR;
-        tg::state_key_kernel<kS><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(slab, (unsigned long long *)keys, B);
+        const long long tiles = (B + (256 / tg::Geo<kS>::WR) - 1) / (256 / tg::Geo<kS>::WR);
+        tg::state_key_kernel<kS><<<(unsigned)(tiles < 148 * 16 ? tiles : 148 * 16), 256, 0, st>>>(slab, (unsigned long long *)keys, B);
     });
     TG_CUDA(cudaGetLastError());
     return TG_OK;

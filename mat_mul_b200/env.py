@@ -136,6 +136,29 @@ def step_batch(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: 
 
 
 # ---------------------------------------------------------------- K2
+def expand_children(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, with_keys: bool = True):
+    """Batched leaf expansion (tg_expand_children): children[b, c] = slab[b] - rank1(tape[b, c]).
+
+    slab int8 (B, GP), tape uint8 (B, k, TP).  Returns (children (B, k, GP), flags (B, k), nnz (B, k), keys (B, k) or
+    None).  Reference: act.py:266-275 get_child_states + the null / terminal / already-in-tree tests of extend_tree
+    (act.py:177-195), for B states at once."""
+    _need_cuda(slab, "slab", torch.int8)
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(S)
+    B = slab.shape[0]
+    if tape.dim() != 3 or tape.shape[0] != B or tape.shape[2] != lay.token_pitch or slab.shape[1] != lay.game_pitch:
+        raise TensorGameError(f"expected slab (B,{lay.game_pitch}) and tape (B,k,{lay.token_pitch})")
+    k = tape.shape[1]
+    dev = slab.device
+    children = torch.empty((B, k, lay.game_pitch), dtype=torch.int8, device=dev)
+    flags = torch.empty((B, k), dtype=torch.uint8, device=dev)
+    nnz = torch.empty((B, k), dtype=torch.int32, device=dev)
+    keys = torch.empty((B, k), dtype=torch.int64, device=dev) if with_keys else None
+    check(_lib.lib().tg_expand_children(_p(slab), _p(tape), k, _p(children), _p(flags), _p(nnz), _p(keys), B, S, shift,
+                                        _stream()), "tg_expand_children")
+    return children, flags, nnz, keys
+
+
 def rollout(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: torch.Tensor | None = None):
     """Apply a step-major tape (K, B, TP) to every game, freezing solved games.
     Returns (out, flags, nnz, steps).  Reference: datasets.py:144-153, training.py:336-342, act.py:49."""

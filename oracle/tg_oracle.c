@@ -710,11 +710,14 @@ static uint64_t splitmix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
+/* key(T) = sum_e T[e] * C_e  (mod 2^64),  C_e = splitmix64(e + 1) | 1,  e the dense index (i*S+j)*S+k: a linear
+ * (multiply-add) hash with one odd 64-bit constant per position.  Linear, so the key of a child state is the key of
+ * its parent minus the contribution of the rank-1 action; the all-zero state has key 0. */
 uint64_t orc_state_key(const int32_t *T, int S) {
     const int S3 = S * S * S;
     uint64_t h = 0;
     for (int e = 0; e < S3; e++)
-        if (T[e] != 0) h += splitmix64(((uint64_t)(uint32_t)(e + 1) << 32) | (uint32_t)T[e]);
+        if (T[e] != 0) h += (uint64_t)(int64_t)T[e] * (splitmix64((uint64_t)(e + 1)) | 1ull);
     return h;
 }
 

@@ -43,4 +43,11 @@ for S, R, N, vals, probs, shift, p in [(4, 7, 1 << 22, (-1, 0, 1), (0.15, 0.7, 0
     idx = torch.randint(0, N * R, (1 << 16,), device="cuda")
     ms = t_ms(lambda: env.demo_samples(tape, slab, idx, S, 2, replay_shift=shift))
     print(f"S={S} demo_sample T=2: {ms:.3f} ms {idx.numel() / ms / 1e6:.4f} G samples/s")
+    nbp = min(N, 1 << 17)
+    tape_bk = tape[:8, :nbp].permute(1, 0, 2).contiguous()  # (B, k=8, TP): the first 8 actions of each demo as candidates
+    ms = t_ms(lambda: env.expand_children(slab[:nbp], tape_bk, S, shift))
+    lay_b = lay.game_pitch * (1 + 1 / 8) + lay.token_pitch + 13
+    print(f"S={S} expand_children k=8: {ms:.3f} ms {nbp * 8 / ms / 1e6:.3f} G children/s hbm_frac={nbp * 8 * lay_b / ms / 1e6 / 6549.1:.3f} (moved bytes)")
+    ms = t_ms(lambda: env.expand_children(slab[:nbp], tape_bk, S, shift, with_keys=False))
+    print(f"S={S} expand_children k=8 (no keys): {ms:.3f} ms {nbp * 8 / ms / 1e6:.3f} G children/s hbm_frac={nbp * 8 * (lay_b - 8) / ms / 1e6 / 6549.1:.3f}")
     del tape, slab, out, rev

@@ -144,3 +144,32 @@ def test_host_path_matches_device_path(env, S):
     want, wflags, wnnz = orc.step_batch(T, tok, shift)
     assert np.array_equal(slab_to_dense(out.numpy(), S), want)
     assert np.array_equal(flags.numpy() & 3, wflags) and np.array_equal(nnz.numpy(), wnnz)
+
+
+@pytest.mark.parametrize("S,B,k,shift", [(4, 1, 1, 1), (4, 777, 8, 1), (9, 13, 3, 2), (9, 500, 8, 2), (16, 5, 2, 2), (16, 67, 8, 2)])
+def test_expand_children_equals_k_single_steps(env, S, B, k, shift):
+    """K8: batched leaf expansion = tg_step on the k-fold replicated parents + tg_state_key of the children."""
+    rng = np.random.default_rng(S * 100 + k)
+    T = rng.integers(-3, 4, (B, S, S, S)) * (rng.random((B, S, S, S)) < 0.15)
+    tok = rng.integers(0, 2 * shift + 1, (B, k, 3 * S))
+    tok[rng.random((B, k, 3 * S)) < 0.5] = shift
+    tok[0, 0] = shift                      # a null action
+    if B > 2:                              # a child that solves the game: parent = the rank-1 tensor of its action
+        f = tok[2, k - 1].reshape(3, S) - shift
+        f[:, 0] = 1
+        tok[2, k - 1] = (f + shift).reshape(-1)
+        T[2] = orc.uvw_to_tensor(f[0], f[1], f[2])
+    slab = torch.from_numpy(dense_to_slab(T)).cuda()
+    tape = torch.from_numpy(np.stack([tokens_to_tape(tok[:, c]) for c in range(k)], axis=1)).cuda().contiguous()
+    children, flags, nnz, keys = env.expand_children(slab, tape, S, shift)
+    rep = slab.unsqueeze(1).expand(B, k, slab.shape[1]).reshape(B * k, -1).contiguous()
+    want, wf, wn = env.step_batch(rep, tape.reshape(B * k, -1).contiguous(), S, shift)
+    assert torch.equal(children.reshape(B * k, -1), want) and torch.equal(flags.reshape(-1), wf)
+    assert torch.equal(nnz.reshape(-1), wn) and torch.equal(keys.reshape(-1), env.state_keys(want, S))
+    # and against the oracle
+    od, of, on = orc.step_batch(np.repeat(T, k, axis=0), tok.reshape(B * k, -1), shift)
+    assert np.array_equal(slab_to_dense(children.reshape(B * k, -1).cpu().numpy(), S), od)
+    assert np.array_equal(flags.reshape(-1).cpu().numpy() & 3, of)
+    assert (flags[0, 0] & 2) and (B <= 2 or (flags[2, k - 1] & 1))
+    c2, f2, n2, k2 = env.expand_children(slab, tape, S, shift, with_keys=False)
+    assert k2 is None and torch.equal(c2, children) and torch.equal(f2, flags)
