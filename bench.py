@@ -146,6 +146,17 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, bar
     ms = _time_ms(lambda: env.demo_samples(tape3, slab, idx, S, 2, replay_shift=shift), 3, torch)
     out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2,
                           "hbm_frac": idx.numel() * (2 * S ** 3 * 4) / (ms * 1e-3) / 1e9 / peak}
+    # batched leaf expansion (K8): k = 8 candidate actions per state, children + flags + nnz (+ keys)
+    nbp = min(B, 1 << 17)
+    tape_bk = tape3[:8, :nbp].permute(1, 0, 2).contiguous()
+    kk = tape_bk.shape[1]
+    moved = lay.game_pitch * (1 + 1 / kk) + lay.token_pitch + 5
+    ms = _time_ms(lambda: env.expand_children(slab[:nbp], tape_bk, S, shift, with_keys=False), 3, torch)
+    ms_k = _time_ms(lambda: env.expand_children(slab[:nbp], tape_bk, S, shift, with_keys=True), 3, torch)
+    out["expand_children"] = {"value": nbp * kk / ms * 1e3, "unit": "children/s", "k": kk, "ms": ms,
+                              "hbm_frac": nbp * kk * moved / (ms * 1e-3) / 1e9 / peak,
+                              "with_state_keys": {"value": nbp * kk / ms_k * 1e3, "ms": ms_k}}
+    del tape_bk
     if S == 9:
         # BASELINE.json quotes the metric at 4x4x4 too: the same two numbers on 2^22 games of the 2x2 matmul size
         # (reference defaults: coefficients {-1,0,1}, P(0) = 0.7, R = 7, shift = 1)
