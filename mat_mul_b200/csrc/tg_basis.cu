@@ -401,33 +401,154 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
     if (live && t == 0) flags[g0 + gl] = fast ? (uint8_t)s_st[3] : BASIS_REDO;
 }
 
-// tokens of one game-step: coef' = M coef for the three factors; token' = coef' + shift_out
+// unsigned bytes of a  x  signed bytes of b, accumulated
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// factors follow the change of basis: coef' = M coef for the three factors of every action; token' = coef' + shift_out.
+// Thread (game n, row i) keeps row i of A, B and C as packed bytes in registers for all R actions of the game; per
+// action it reads the token record once (128-bit loads), takes each factor's S tokens with static funnel shifts and
+// needs ceil(S/4) DP4A (unsigned tokens x signed matrix row; the input shift is folded in through the row sum).
 template <int S>
-__global__ void basis_factors_kernel(const uint8_t *__restrict__ tape_in, long long in_step_stride, int shift_in,
-                                     const int8_t *__restrict__ mats, long long mat_stride, uint8_t *__restrict__ tape_out,
-                                     long long out_step_stride, int shift_out, uint8_t *__restrict__ flags, long long N,
-                                     int R) {
+__global__ void __launch_bounds__(256)
+    basis_factors_kernel(const uint8_t *__restrict__ tape_in, long long in_step_stride, int shift_in,
+                         const int8_t *__restrict__ mats, long long mat_stride, uint8_t *__restrict__ tape_out,
+                         long long out_step_stride, int shift_out, uint8_t *__restrict__ flags, long long N, int R) {
     using G = Geo<S>;
-    // thread = (game n, step r, output token q in [0, TP))
-    const long long total = N * (long long)R * G::TP;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(idx % G::TP);
-        const long long nr = idx / G::TP;
-        const long long n = nr % N;
-        const int r = (int)(nr / N);
-        uint8_t tokv = 0;
-        if (q < 3 * S) {
-            const int f = q / S, i = q % S;
-            const uint8_t *tin = tape_in + (size_t)r * in_step_stride + n * G::TP + f * S;
-            const int8_t *M = mats + n * mat_stride + f * S * S + i * S;
-            int acc = 0;
+    constexpr int GPB = 256 / S, KW4 = (S + 3) / 4, NWT = G::TP / 4;
+    constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu;
+    const int gl = threadIdx.x / S, i = threadIdx.x % S;
+    if (gl >= GPB) return;
+    for (long long n = (long long)blockIdx.x * GPB + gl; n < N; n += (long long)gridDim.x * GPB) {
+        uint32_t mrow[3][KW4];
+        int rowsum[3];
 #pragma unroll
-            for (int a = 0; a < S; a++) acc += (int)M[a] * ((int)tin[a] - shift_in);
-            if (acc < -shift_out || acc > shift_out) flags[n] |= (uint8_t)TG_FLAG_TOKEN_RANGE; // same bit from every writer
-            tokv = (uint8_t)(acc + shift_out);
+        for (int f = 0; f < 3; f++) {
+            const int8_t *M = mats + n * mat_stride + f * S * S + i * S;
+            rowsum[f] = 0;
+#pragma unroll
+            for (int m = 0; m < KW4; m++) mrow[f][m] = 0;
+#pragma unroll
+            for (int a = 0; a < S; a++) {
+                const int v = (int)M[a];
+                rowsum[f] += v;
+                mrow[f][a >> 2] |= ((uint32_t)v & 0xFFu) << (8 * (a & 3));
+            }
         }
-        tape_out[(size_t)r * out_step_stride + n * G::TP + q] = tokv;
+        bool bad = false;
+        // the record of action r+1 is in flight while action r is transformed
+        uint4 nxt[NWT / 4];
+        {
+            const uint4 *src0 = reinterpret_cast<const uint4 *>(tape_in + n * G::TP);
+#pragma unroll
+            for (int q = 0; q < NWT / 4; q++) nxt[q] = src0[q];
+        }
+        for (int r = 0; r < R; r++) {
+            uint32_t w[NWT + 1];
+#pragma unroll
+            for (int q = 0; q < NWT / 4; q++)
+                w[4 * q] = nxt[q].x, w[4 * q + 1] = nxt[q].y, w[4 * q + 2] = nxt[q].z, w[4 * q + 3] = nxt[q].w;
+            w[NWT] = 0;
+            if (r + 1 < R) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(tape_in + (size_t)(r + 1) * in_step_stride + n * G::TP);
+#pragma unroll
+                for (int q = 0; q < NWT / 4; q++) nxt[q] = src[q];
+            }
+            uint8_t *dst = tape_out + (size_t)r * out_step_stride + n * G::TP;
+#pragma unroll
+            for (int f = 0; f < 3; f++) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int o = f * S; // byte offset of the factor's tokens in the record (compile time after unrolling)
+                int acc = -shift_in * rowsum[f];
+#pragma unroll
+                for (int m = 0; m < KW4; m++) {
+                    uint32_t tw = w[(o >> 2) + m];
+                    if ((o & 3) != 0) tw = __funnelshift_r(tw, w[(o >> 2) + m + 1], 8 * (o & 3));
+                    if (m == KW4 - 1) tw &= WLAST;
+                    acc = dp4a_us(tw, mrow[f][m], acc);
+                }
+                bad |= (acc < -shift_out) | (acc > shift_out);
+                dst[o + i] = (uint8_t)(acc + shift_out);
+            }
+            if (3 * S + i < G::TP) dst[3 * S + i] = 0; // tape padding stays zero
+        }
+        if (bad) flags[n] |= (uint8_t)TG_FLAG_TOKEN_RANGE; // same bit from every writer
+    }
+}
+
+// S = 16: a factor's 16 tokens are one aligned 16-byte block, so a thread can own FOUR consecutive rows of one
+// factor's matrix (16 registers), read just that block per action and store its four output tokens as one word.
+__global__ void __launch_bounds__(252)
+    basis_factors16_kernel(const uint8_t *__restrict__ tape_in, long long in_step_stride, int shift_in,
+                           const int8_t *__restrict__ mats, long long mat_stride, uint8_t *__restrict__ tape_out,
+                           long long out_step_stride, int shift_out, uint8_t *__restrict__ flags, long long N, int R) {
+    constexpr int S = 16, TPG = 12, GPB = 252 / TPG, TP = 48;
+    const int gl = threadIdx.x / TPG, t = threadIdx.x % TPG;
+    const int f = t >> 2, i0 = 4 * (t & 3); // factor, first of the four rows
+    for (long long n = (long long)blockIdx.x * GPB + gl; n < N; n += (long long)gridDim.x * GPB) {
+        uint32_t mrow[4][4];
+        int rowsum[4];
+        const int8_t *M = mats + n * mat_stride + f * S * S + i0 * S; // four consecutive rows = 64 contiguous bytes
+        if ((((uintptr_t)mats | (uintptr_t)mat_stride) & 15) == 0) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+                const uint4 v4 = reinterpret_cast<const uint4 *>(M)[ii];
+                mrow[ii][0] = v4.x, mrow[ii][1] = v4.y, mrow[ii][2] = v4.z, mrow[ii][3] = v4.w;
+            }
+        } else {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) word |= ((uint32_t)(uint8_t)M[ii * S + 4 * m + b]) << (8 * b);
+                    mrow[ii][m] = word;
+                }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) {
+            int rs = 0;
+#pragma unroll
+            for (int m = 0; m < 4; m++) rs = __dp4a((int)mrow[ii][m], 0x01010101, rs);
+            rowsum[ii] = rs;
+        }
+        bool bad = false;
+        // the steps of a game are N*TP bytes apart (step-major tape): every load is a fresh DRAM page, so the loop keeps
+        // PF of them in flight per thread (bytes in flight, not instructions, bound this kernel)
+        constexpr int PF = 4;
+        const uint8_t *src = tape_in + n * TP + 16 * f;
+        uint4 ring[PF];
+#pragma unroll
+        for (int q = 0; q < PF; q++)
+            ring[q] = q < R ? *reinterpret_cast<const uint4 *>(src + (size_t)q * in_step_stride) : make_uint4(0, 0, 0, 0);
+        for (int r0 = 0; r0 < R; r0 += PF) {
+#pragma unroll
+            for (int q = 0; q < PF; q++) {
+                const int r = r0 + q;
+                if (r < R) {
+                    const uint4 cur = ring[q];
+                    if (r + PF < R) ring[q] = *reinterpret_cast<const uint4 *>(src + (size_t)(r + PF) * in_step_stride);
+                    uint32_t outw = 0;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ii++) {
+                        int acc = -shift_in * rowsum[ii];
+                        acc = dp4a_us(cur.x, mrow[ii][0], acc);
+                        acc = dp4a_us(cur.y, mrow[ii][1], acc);
+                        acc = dp4a_us(cur.z, mrow[ii][2], acc);
+                        acc = dp4a_us(cur.w, mrow[ii][3], acc);
+                        bad |= (acc < -shift_out) | (acc > shift_out);
+                        outw |= ((uint32_t)(acc + shift_out) & 0xFFu) << (8 * ii);
+                    }
+                    *reinterpret_cast<uint32_t *>(tape_out + (size_t)r * out_step_stride + n * TP + 16 * f + i0) = outw;
+                }
+            }
+        }
+        if (bad) flags[n] |= (uint8_t)TG_FLAG_TOKEN_RANGE; // same bit from every writer
     }
 }
 
@@ -521,12 +642,19 @@ int tg_change_of_basis_factors(const uint8_t *tape_in, int64_t in_step_stride, i
     if (!tape_in || !mats || !tape_out || !flags) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long ms = per_game ? 3LL * S * S : 0;
-    const long long total = N * (long long)R * ((3 * S + 15) & ~15);
-    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    const long long blocks = (N + (256 / S) - 1) / (256 / S);
+    const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+    if (((uintptr_t)tape_in | (uintptr_t)in_step_stride) & 15) return TG_E_ARG;
     switch (S) {
     case 4: tg::basis_factors_kernel<4><<<grid, 256, 0, st>>>(tape_in, in_step_stride, shift_in, mats, ms, tape_out, out_step_stride, shift_out, flags, N, R); break;
     case 9: tg::basis_factors_kernel<9><<<grid, 256, 0, st>>>(tape_in, in_step_stride, shift_in, mats, ms, tape_out, out_step_stride, shift_out, flags, N, R); break;
-    case 16: tg::basis_factors_kernel<16><<<grid, 256, 0, st>>>(tape_in, in_step_stride, shift_in, mats, ms, tape_out, out_step_stride, shift_out, flags, N, R); break;
+    case 16: {
+        const long long b16 = (N + 20) / 21;
+        if ((((uintptr_t)tape_out | (uintptr_t)out_step_stride) & 3) == 0)
+            tg::basis_factors16_kernel<<<(int)(b16 < 148 * 16 ? b16 : 148 * 16), 252, 0, st>>>(tape_in, in_step_stride, shift_in, mats, ms, tape_out, out_step_stride, shift_out, flags, N, R);
+        else
+            tg::basis_factors_kernel<16><<<grid, 256, 0, st>>>(tape_in, in_step_stride, shift_in, mats, ms, tape_out, out_step_stride, shift_out, flags, N, R);
+    } break;
     }
     TG_CUDA(cudaGetLastError());
     return TG_OK;
