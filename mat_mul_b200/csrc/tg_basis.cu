@@ -566,35 +566,91 @@ __device__ __forceinline__ void philox_block(uint32_t c0, uint32_t c1, uint32_t 
 
 // one thread per (game, matrix): M = L * U, L unit-lower, U upper with diagonal +-1, off-diagonal entries
 // -1/0/+1 with probabilities (p_nz/2, 1-p_nz, p_nz/2).  Draw for entry (r,c): byte (r*S+c)%16 of Philox block
-// (r*S+c)/16 with ctr = (block, matrix f, 0x6D617473, d_lo), key as in demo generation.
+// (r*S+c)/16 with ctr = (block, matrix f, 0x6D617473, d_lo), key as in the unimodular contract of the oracle.
+// Everything stays in registers as packed bytes: the draws of a row become its L and U rows with SWAR compares, and
+// row r of M is sum_{k<=r} L[r][k] * (row k of U) -- one IMAD per four entries (entries of M are at most S in size).
 template <int S>
-__global__ void unimodular_kernel(unsigned long long seed, unsigned long long first, long long N, uint32_t thr_nz,
-                                  int8_t *__restrict__ mats) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= N * 3) return;
-    const long long n = t / 3;
+__global__ void __launch_bounds__(64)
+    unimodular_kernel(unsigned long long seed, unsigned long long first, long long N, uint32_t thr_nz, int8_t *__restrict__ mats) {
+    constexpr int NB = (S * S + 15) / 16, KW4 = (S + 3) / 4;
+    // S not a multiple of 4: the S*S-byte matrices of the block's 64 threads are assembled in shared memory and leave
+    // as coalesced words (64 * S * S is a multiple of 4)
+    __shared__ __align__(16) uint8_t s_out[(S % 4) ? 64 * S * S : 16];
+    const long long t0 = blockIdx.x * (long long)blockDim.x;
+    const long long t = t0 + threadIdx.x;
+    const bool live = t < N * 3;
+    const long long n = live ? t / 3 : 0;
     const int f = (int)(t % 3);
     const unsigned long long d = first + (unsigned long long)n;
     const uint32_t k0 = (uint32_t)seed ^ ((uint32_t)(d >> 32) * 0x9E3779B9u), k1 = (uint32_t)(seed >> 32);
-    int8_t L[S * S], U[S * S];
-    uint32_t blk[4] = {0, 0, 0, 0};
-    for (int e = 0; e < S * S; e++) {
-        if ((e & 15) == 0) philox_block((uint32_t)(e >> 4), (uint32_t)f, 0x6D617473u, (uint32_t)d, k0, k1, blk);
-        const uint32_t byte = (blk[(e >> 2) & 3] >> (8 * (e & 3))) & 0xFFu;
-        const int r = e / S, c = e % S;
-        // low 7 bits: non-zero?  top bit: sign
-        const int mag = (byte & 0x7Fu) < thr_nz ? 1 : 0;
-        const int val = (byte & 0x80u) ? -mag : mag;
-        L[e] = (int8_t)(r > c ? val : (r == c ? 1 : 0));
-        U[e] = (int8_t)(r < c ? val : (r == c ? ((byte & 0x80u) ? -1 : 1) : 0));
-    }
-    int8_t *out = mats + (n * 3 + f) * S * S;
-    for (int r = 0; r < S; r++)
-        for (int c = 0; c < S; c++) {
-            int acc = 0;
-            for (int k = 0; k < S; k++) acc += (int)L[r * S + k] * (int)U[k * S + c];
-            out[r * S + c] = (int8_t)acc;
+    uint32_t dw[4 * NB + 1];
+#pragma unroll
+    for (int b = 0; b < NB; b++) philox_block((uint32_t)b, (uint32_t)f, 0x6D617473u, (uint32_t)d, k0, k1, &dw[4 * b]);
+    dw[4 * NB] = 0;
+    const uint32_t cthr = (0x80u - (thr_nz > 0x80u ? 0x80u : thr_nz)) * ONES4; // (draw & 0x7F) + cthr sets bit 7 iff >= thr
+    int32_t urow[S][KW4]; // rows of U in integer form (sum_b x_b 256^b)
+    int8_t *out = (S % 4) ? reinterpret_cast<int8_t *>(s_out) + threadIdx.x * S * S : mats + (n * 3 + f) * S * S;
+    if ((S % 4) == 0 && !live) return;
+#pragma unroll
+    for (int r = 0; r < S; r++) {
+        uint32_t lrow[KW4];
+        int32_t acc[KW4];
+#pragma unroll
+        for (int m = 0; m < KW4; m++) {
+            // the draw bytes of entries (r, 4m .. 4m+3)
+            const int o = r * S + 4 * m;
+            uint32_t x = dw[o >> 2];
+            if ((o & 3) != 0) x = __funnelshift_r(x, dw[(o >> 2) + 1], 8 * (o & 3));
+            uint32_t colmask = 0, lowmask = 0, highmask = 0, diag = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int c = 4 * m + b;
+                if (c < S) colmask |= 0xFFu << (8 * b);
+                if (c < r) lowmask |= 0xFFu << (8 * b);
+                if (c > r && c < S) highmask |= 0xFFu << (8 * b);
+                if (c == r) diag |= 0xFFu << (8 * b);
+            }
+            const uint32_t notmag = ((x & 0x7F7F7F7Fu) + cthr) & H4;      // bit 7 set where the magnitude is 0
+            const uint32_t magmask = (((notmag ^ H4) >> 7) * 0xFFu) & colmask;
+            const uint32_t negmask = ((x & H4) >> 7) * 0xFFu;
+            const uint32_t sgn1 = negmask | ONES4;                        // -1 or +1 in every byte
+            const uint32_t val = magmask & sgn1;
+            lrow[m] = (val & lowmask) | (ONES4 & diag);
+            const uint32_t ub = (val & highmask) | (sgn1 & diag);
+            urow[r][m] = (int32_t)((ub ^ H4) - H4);
+            acc[m] = 0;
         }
+#pragma unroll
+        for (int k = 0; k <= r; k++) {
+            const uint32_t w = lrow[k >> 2];
+            const int l = (int)(int8_t)((w >> (8 * (k & 3))) & 0xFFu);
+#pragma unroll
+            for (int m = 0; m < KW4; m++) acc[m] += l * urow[k][m];
+        }
+        uint32_t words[KW4];
+#pragma unroll
+        for (int m = 0; m < KW4; m++) words[m] = ((uint32_t)acc[m] + H4) ^ H4;
+        if constexpr (S % 4 == 0) {
+#pragma unroll
+            for (int m = 0; m < KW4; m++) reinterpret_cast<uint32_t *>(out + r * S)[m] = words[m];
+        } else {
+#pragma unroll
+            for (int c = 0; c < S; c++) out[r * S + c] = (int8_t)(words[c >> 2] >> (8 * (c & 3)));
+        }
+    }
+    if constexpr ((S % 4) != 0) {
+        __syncthreads();
+        const long long nlive = min((long long)blockDim.x, N * 3 - t0); // matrices of this block
+        const long long bytes = nlive * S * S;
+        int8_t *dst = mats + t0 * S * S;
+        if ((((uintptr_t)dst) & 3) == 0) {
+            for (long long w = threadIdx.x; w < bytes / 4; w += blockDim.x)
+                reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<const uint32_t *>(s_out)[w];
+            for (long long b = (bytes & ~3LL) + threadIdx.x; b < bytes; b += blockDim.x) dst[b] = (int8_t)s_out[b];
+        } else {
+            for (long long b = threadIdx.x; b < bytes; b += blockDim.x) dst[b] = (int8_t)s_out[b];
+        }
+    }
 }
 
 } // namespace tg
