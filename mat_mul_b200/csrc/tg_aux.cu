@@ -177,12 +177,17 @@ __global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__re
         const uint32_t pv = __shfl_sync(0xFFFFFFFFu, row[c], pl);
         const uint32_t mine = row[c];
         const bool elim = has && !used && lane != pl && mine != 0;
+        // columns <= c of the rows still in play are zero from here on: only k > c needs the update
+        //   row[k] <- row[k] * pv - mine * pk  =  row[k] * pv + (P - mine) * pk   (mod P), one reduction for both products
+        const uint32_t nmine = P - mine;
 #pragma unroll
-        for (int k = 0; k < S; k++) {
+        for (int k = c + 1; k < S; k++) {
             const uint32_t pk = __shfl_sync(0xFFFFFFFFu, row[k], pl);
             if (elim) {
-                const uint32_t x = mulmod31(row[k], pv), y = mulmod31(mine, pk);
-                row[k] = x >= y ? x - y : x + P - y;
+                const unsigned long long z = (unsigned long long)row[k] * pv + (unsigned long long)nmine * pk; // < 2^63
+                unsigned long long r = (z & 0x7FFFFFFFull) + (z >> 31);                                        // < 2^33
+                uint32_t q = (uint32_t)(r & 0x7FFFFFFFull) + (uint32_t)(r >> 31);
+                row[k] = q >= P ? q - P : q;
             }
         }
         if (has && lane == pl) used = true;
