@@ -173,3 +173,35 @@ def test_expand_children_equals_k_single_steps(env, S, B, k, shift):
     assert (flags[0, 0] & 2) and (B <= 2 or (flags[2, k - 1] & 1))
     c2, f2, n2, k2 = env.expand_children(slab, tape, S, shift, with_keys=False)
     assert k2 is None and torch.equal(c2, children) and torch.equal(f2, flags)
+
+
+def test_new_entry_points_empty_and_bad_args(env):
+    """N = 0 is a no-op; wrong sizes / misaligned pointers / unsupported shapes come back as TG_E_ARG, never a crash."""
+    from mat_mul_b200 import _lib
+    from mat_mul_b200.env import _p, _stream
+
+    L = _lib.lib()
+    S = 9
+    lay = env.layout(S)
+    slab = torch.zeros((4, lay.game_pitch), dtype=torch.int8, device="cuda")
+    tape = torch.full((4, 2, lay.token_pitch), 2, dtype=torch.uint8, device="cuda")
+    tape[:, :, 3 * S:] = 0
+    kids = torch.empty((4, 2, lay.game_pitch), dtype=torch.int8, device="cuda")
+    fl = torch.empty((4, 2), dtype=torch.uint8, device="cuda")
+    nz = torch.empty((4, 2), dtype=torch.int32, device="cuda")
+    assert L.tg_expand_children(_p(slab), _p(tape), 2, _p(kids), _p(fl), _p(nz), None, 0, S, 2, _stream()) == 0       # B = 0
+    assert L.tg_expand_children(_p(slab), _p(tape), 0, _p(kids), _p(fl), _p(nz), None, 4, S, 2, _stream()) != 0       # k = 0
+    assert L.tg_expand_children(_p(slab), _p(tape), 2, _p(kids), _p(fl), _p(nz), None, 4, 5, 2, _stream()) != 0       # S = 5
+    assert L.tg_expand_children(slab.data_ptr() + 1, _p(tape), 2, _p(kids), _p(fl), _p(nz), None, 4, S, 2, _stream()) != 0
+    assert L.tg_expand_children(_p(slab), _p(tape), 100000, _p(kids), _p(fl), _p(nz), None, 4, S, 2, _stream()) != 0  # smem
+    c, f, n, k = env.expand_children(slab, tape, S, 2)  # null actions on the zero state: terminal and null
+    torch.cuda.synchronize()
+    assert not c.any() and bool(((f & 3) == 3).all()) and not n.any() and not k.any()
+    # tensor-core accumulate: only S = 16 and R <= 64
+    t16 = torch.zeros((65, 3, 48), dtype=torch.uint8, device="cuda")
+    s16 = torch.empty((3, 4096), dtype=torch.int8, device="cuda")
+    f16 = torch.empty(3, dtype=torch.uint8, device="cuda")
+    assert L.tg_demo_accumulate_tc(_p(t16), 3 * 48, 3, 65, 16, 2, _p(s16), _p(f16), _stream()) != 0
+    assert L.tg_demo_accumulate_tc(_p(t16), 3 * 48, 3, 64, 9, 2, _p(s16), _p(f16), _stream()) != 0
+    assert L.tg_demo_accumulate_tc(_p(t16), 3 * 48, 0, 64, 16, 2, _p(s16), _p(f16), _stream()) == 0
+    torch.cuda.synchronize()
