@@ -29,6 +29,8 @@
 //      R * shift^3 a per-thread bound shift^2 * sum_r |v_rj| guards the packed
 //      path and the (rare) thread above it recomputes its entries one by one.
 //   C. the slab tile leaves through one TMA bulk store.
+#include <cstdlib>
+
 #include "tg_step.cuh"
 
 namespace tg {
@@ -179,7 +181,7 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
 }
 
 template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD>
-__global__ void __launch_bounds__(NT, S == 16 ? 2 : (S == 9 ? 5 : 4))
+__global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 5 : 4))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
                 long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags) {
@@ -472,12 +474,39 @@ template <bool SAMPLE, int NTHR>
 static int dispatch_demo(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
                          int max_tries, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     switch (S) {
-    case 4: // big tiles (4 passes of phase B) amortise the retry tail of the sampler; long action lists fall back
+    case 4: { // big tiles (several passes of phase B) amortise the retry tail of the sampler; long action lists fall back
+        static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+        if (variant == 1 && DemoCfg<4, 128, 8>::smem_bytes(R) <= 160 * 1024)
+            return launch_demo<4, 128, 8, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        if (variant == 2 && DemoCfg<4, 128, 4>::smem_bytes(R) <= 160 * 1024)
+            return launch_demo<4, 128, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        if (variant == 3 && DemoCfg<4, 512, 2>::smem_bytes(R) <= 160 * 1024)
+            return launch_demo<4, 512, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
             return launch_demo<4, 256, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         return launch_demo<4, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    case 9: return launch_demo<9, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    case 16: return launch_demo<16, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    }
+    case 9: {
+        static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+        switch (variant) {
+        case 1: return launch_demo<9, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        case 2: return launch_demo<9, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        case 3: return launch_demo<9, 128, 3, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        case 4: return launch_demo<9, 192, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        case 5: return launch_demo<9, 64, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        default: // measured best (profiles/README.md): 128-thread CTAs; 28-demo tiles when sampling, 14-demo tiles (slab tile
+                 // overlaid on the records) when only accumulating
+            if (SAMPLE) return launch_demo<9, 128, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+            return launch_demo<9, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        }
+    }
+    case 16: {
+        static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+        if (variant == 1) return launch_demo<16, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        if (variant == 2) return launch_demo<16, 64, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        if (variant == 3) return launch_demo<16, 128, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        return launch_demo<16, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st); // measured best
+    }
     }
     return TG_E_ARG;
 }
