@@ -30,6 +30,8 @@
 // int8 matrices); a thread owns one column of the contracted axis in registers
 // and produces its S outputs.  TG_FLAG_RANGE marks games whose T' leaves the
 // int8 slab's guaranteed zone [-64,63].
+#include <cstdlib>
+
 #include "tg_common.cuh"
 
 namespace tg {
@@ -61,7 +63,6 @@ __device__ __forceinline__ void mode_pass(const int32_t *__restrict__ in, int32_
     }
 }
 
-constexpr uint8_t BASIS_REDO = 0x80; // internal: set by the fast kernel, cleared by the exact one
 
 // only_marked: visit every game, redo those the fast kernel marked with BASIS_REDO
 template <int S>
@@ -680,6 +681,17 @@ int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, 
         tg::basis_kernel<SS><<<flags ? exact_grid : (int)N, tg::BasisCfg<SS>::NT, tg::BasisCfg<SS>::SMEM_BYTES, st>>>(  \
             slab_in, mats, ms, slab_out, flags, N, flags ? 1 : 0);                                                     \
     } break;
+    // S = 16: the tensor-core kernel (tg_basis_mma.cu) takes the place of the packed fast kernel; TG_BASIS_VARIANT=1
+    // keeps the packed kernel (A/B timing only)
+    static const int variant = getenv("TG_BASIS_VARIANT") ? atoi(getenv("TG_BASIS_VARIANT")) : 0;
+    if (S == 16 && flags && variant != 1 && (((uintptr_t)mats | (uintptr_t)ms) & 3) == 0) {
+        const int rc = tg::launch_basis_mma16(slab_in, mats, ms, slab_out, flags, N, st);
+        if (rc != TG_OK) return rc;
+        tg::basis_kernel<16><<<exact_grid, tg::BasisCfg<16>::NT, tg::BasisCfg<16>::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out,
+                                                                                                 flags, N, 1);
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
     switch (S) {
         TG_BASIS_CASE(4)
         TG_BASIS_CASE(9)

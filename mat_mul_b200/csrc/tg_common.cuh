@@ -36,6 +36,12 @@ inline int cuda_fail(cudaError_t e) {
         if (_e != cudaSuccess) return tg::cuda_fail(_e); \
     } while (0)
 
+// change of basis: set by a fast kernel on the games it leaves to the exact int32 kernel, which clears it
+constexpr uint8_t BASIS_REDO = 0x80;
+// tg_basis_mma.cu: 16x16x16 games, one warp per game on mma.sync int8
+int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, int8_t *slab_out, uint8_t *flags,
+                       long long N, cudaStream_t st);
+
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA 1-D)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

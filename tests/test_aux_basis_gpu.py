@@ -154,3 +154,45 @@ def test_change_of_basis_large_matrices_take_the_exact_path(env, S, amp, dens):
     assert ok.sum() >= N // 5
     assert np.array_equal(slab_to_dense(out.cpu().numpy()[ok], S), want[ok])
     assert np.array_equal(slab_to_dense(out.cpu().numpy(), S).astype(np.int8), want.astype(np.int8))  # low byte always
+
+
+def test_change_of_basis_tensor_core_path_16(env):
+    # S = 16 runs on mma.sync (tg_basis_mma.cu): modulo-2^16 byte planes, exact range flag under its norm guard, the
+    # exact int32 kernel for the games the guard rejects.  Mix of identity / permutation / sparse unimodular /
+    # denser matrices and extreme int8 entries; the result is the int64 einsum either way.
+    S, N = 16, 403
+    rng = np.random.default_rng(16)
+    T = rng.integers(-25, 26, (N, S, S, S)) * (rng.random((N, S, S, S)) < 0.4)
+    T[5] = rng.integers(-128, 128, (S, S, S))
+    T[6] = -128
+    T[7] = 127
+    T[8] = 0
+    m = np.zeros((N, 3, S, S), dtype=np.int64)
+    uni = orc.sample_unimodular(3, 0, N, S, 0.03)
+    for n in range(N):
+        kind = n % 6
+        if kind == 0:
+            m[n] = np.eye(S, dtype=np.int64)
+        elif kind == 1:
+            m[n] = np.stack([np.eye(S, dtype=np.int64)[rng.permutation(S)] * rng.choice([-1, 1], (S, 1)) for _ in range(3)])
+        elif kind in (2, 3):
+            m[n] = uni[n]
+        elif kind == 4:
+            m[n] = np.eye(S, dtype=np.int64) + rng.integers(-1, 2, (3, S, S)) * (rng.random((3, S, S)) < 0.04)
+        else:
+            m[n] = rng.integers(-3, 4, (3, S, S)) * (rng.random((3, S, S)) < 0.3)
+    m[9, 2] = -128  # ||C||inf far beyond the guard
+    m[10, 0, 3] = 127
+    slab = torch.from_numpy(dense_to_slab(T)).cuda()
+    out, flags = env.change_of_basis(slab, torch.from_numpy(m.astype(np.int8)).cuda(), S)
+    want = np.einsum("nia,njb,nkc,nabc->nijk", m[:, 0], m[:, 1], m[:, 2], T)
+    f = flags.cpu().numpy()
+    assert not (f & 0x80).any()
+    assert np.array_equal((f & 4) != 0, ((want < -64) | (want > 63)).reshape(N, -1).any(1))
+    assert np.array_equal(f & ~np.uint8(4), np.zeros(N, dtype=np.uint8))
+    assert np.array_equal(slab_to_dense(out.cpu().numpy(), S).astype(np.int8), want.astype(np.int8))
+    # one shared triple for every game
+    out1, f1 = env.change_of_basis(slab, torch.from_numpy(m[2].astype(np.int8)).cuda(), S)
+    want1 = np.einsum("ia,jb,kc,nabc->nijk", m[2, 0], m[2, 1], m[2, 2], T)
+    assert np.array_equal(slab_to_dense(out1.cpu().numpy(), S).astype(np.int8), want1.astype(np.int8))
+    assert np.array_equal((f1.cpu().numpy() & 4) != 0, ((want1 < -64) | (want1 > 63)).reshape(N, -1).any(1))
