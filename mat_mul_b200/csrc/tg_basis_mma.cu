@@ -4,37 +4,49 @@
 // ABSENT from the reference; spec as in tg_basis.cu:
 //     T'[i][j][k] = sum_abc A[i][a] B[j][b] C[k][c] T[a][b][c]
 //
-// One WARP per game, three passes of  mma.sync.m16n8k16 (int8 x int8 -> int32), the
-// 16x16 matrix always the A operand (M = the new index), the tensor the B
-// operand (K = the contracted index, N = 8 values of one surviving index):
-//   1. Y[k'][a][b] = sum_c C[k'][c] T[a][b][c]   B fragment = a slab word as it lies in HBM
-//      (lane (g,t) reads word (a*16 + 8h + g)*4 + t: one coalesced 128-byte line per MMA);
+// One WARP per game, three passes of mma.sync m16n8k16, the 16x16 matrix always
+// the A operand (M = the new index), the tensor the B operand (K = the contracted
+// index, N = 8 values of one surviving index):
+//   1. Y[k'][a][b] = sum_c C[k'][c] T[a][b][c]   int8 MMA; B fragment = a slab word as it lies in
+//      HBM (lane (g,t) reads word (a*16 + 8h + g)*4 + t: one coalesced 128-byte line per MMA);
 //   2. Z[j'][a][k'] = sum_b B[j'][b] Y[k'][a][b]  the accumulators of two pass-1 MMAs ARE the
-//      next B fragment (column g <-> k' = g, K slots 4t..4t+3 <-> b = 2t, 2t+1, 8+2t, 9+2t;
-//      the columns of matrix B are permuted the same way when its fragment is built);
+//      next B fragment (column g <-> k' = g; K slots <-> the b of the two tiles);
 //   3. T'[i'][j'][k'] = sum_a A[i'][a] Z[j'][a][k']  needs a on the K slots of a lane while
-//      pass 2 leaves it spread over MMAs: the one real transposition, through 10 KB of
+//      pass 2 leaves it spread over MMAs: the one real transposition, through 11 KB of
 //      shared memory per warp (16 STS.128 + 16 LDS.128 per lane, conflict-free pitches).
-// Operands wider than int8: arithmetic modulo 2^16 is a ring homomorphism, so each
-// later pass feeds the low 16 bits of its input as two byte planes,
-//     M x = M lo(x) [s8 x u8]  +  256 * M hi(x) [s8 x s8]      (mod 2^16)
-// i.e. two MMAs chained through the accumulator (one IMAD per register in between).
-// The int8 output (T' mod 256) is therefore always right; the TG_FLAG_RANGE test
-// reads the 16-bit results and is exact iff every true |T'| <= 32767, which is
-// guaranteed up front by  ||C||inf <= 255  (Y fits 16 bits) and
-// ybound * ||A||inf * ||B||inf <= 32767  with ybound >= max|Y| read off the high byte
-// plane.  A game that fails the test is marked BASIS_REDO and redone by the exact
-// int32 kernel of tg_basis.cu -- results are identical either way.
+// Y and Z do not fit int8.  Two ways to feed them to the next pass, chosen per game
+// (warp-uniform), both bit-identical to the int64 oracle:
+//   F16: passes 2 and 3 are f16 MMAs with f32 accumulation -- exact integer arithmetic while
+//        |Y|, |Z| <= 2048 (f16 holds those integers, the f32 sums stay below 2^24).  The int32
+//        accumulators of pass 1 start at the bit pattern of 1.5 * 2^23, so they are floats already
+//        (one FADD removes the offset); accumulators become the next operand with one
+//        cvt.rn.f16x2.f32 per two values; pass 3 starts at 1.5 * 2^23 again, so the low byte of its
+//        accumulators is the int8 result.  Guard (a priori, tb >= max|T| from the OR of the byte
+//        magnitudes):  tb ||C|| <= 2048,  tb ||C|| ||B|| <= 2048,  tb ||C|| ||B|| ||A|| <= 32767.
+//   P16: int8 MMAs on the low 16 bits as two byte planes (arithmetic modulo 2^16 is a ring
+//        homomorphism):  M x = M lo8(x) [s8 x u8] + 256 * M hi8(x) [s8 x s8], two MMAs chained through
+//        the accumulator.  T' mod 256 is always right; the range flag reads the 16-bit results and
+//        is exact iff |T'| <= 32767, guaranteed by ||C|| <= 255 (Y fits 16 bits) and
+//        ybound ||A|| ||B|| <= 32767 with ybound >= max|Y| read off the high byte plane.
+//   else the game is marked BASIS_REDO and redone by the exact int32 kernel of tg_basis.cu.
+// Why not int8 MMAs throughout: every legacy MMA shape issues at 0.49 per clock and SM
+// (scripts/ubench_pipes.cu), and the byte-plane marshaling (PRMT) saturates the ALU pipe;
+// cvt.rn.f16x2.f32 issues beside it (profiles/README.md).
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "tg_common.cuh"
 
 namespace tg {
 
 namespace {
 
-constexpr int PQ = 20;              // words between the a-quads of one (plane, j') row: 16 + 4 (bank spread)
-constexpr int PJ = 4 * PQ;          // words between j' rows
-constexpr int PP = 16 * PJ;         // words between the two byte planes
-constexpr int WARP_WORDS = 2 * PP;  // 2560 words = 10 KB per warp
+// transposition buffer of a warp: word (j', slot, pos), slot = plane * 4 + a / 4 (P16) or a / 2 (F16), pos = 4t + the
+// lane's k' position; pitches chosen so that neither the 128-bit stores nor the 128-bit loads conflict
+constexpr int PQ = 20;              // words between slots: 16 + 4
+constexpr int PJ = 8 * PQ + 16;     // words between j' rows (176 = 16 mod 32)
+constexpr int WARP_WORDS = 16 * PJ; // 2816 words = 11 KB per warp
 constexpr int WARPS = 4;            // games per CTA
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -72,6 +84,37 @@ __device__ __forceinline__ void pack_planes(int v0, int v1, int v2, int v3, uint
     hi = prmt(p01, p23, 0x7632u);
 }
 
+// d += A(f16, 16x16) * B(f16, 16x8), f32 accumulation
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// (lo, hi) -> f16x2 word, lo in the low half
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// int8 bytes b0, b1 of w (as selected by the caller) -> f16x2
+__device__ __forceinline__ uint32_t bytes_to_f16(uint32_t w, int b0, int b1) {
+    return pack_f16((float)(int8_t)(w >> (8 * b0)), (float)(int8_t)(w >> (8 * b1)));
+}
+
+constexpr float MAGIC = 12582912.0f;     // 1.5 * 2^23: float(MAGIC + n) has n in its low mantissa bits
+constexpr int MAGIC_BITS = 0x4B400000;
+
+// one's complement magnitude of the four int8 of w (|x| <= mag + 1), for OR-accumulated bounds
+__device__ __forceinline__ uint32_t mag4(uint32_t w) { return w ^ prmt(w, 0u, 0xBA98u); }
+
+// OR of the four bytes of w, over the warp
+__device__ __forceinline__ int warp_or_bytes(uint32_t w) {
+    w |= w >> 16;
+    w |= w >> 8;
+    return (int)__reduce_or_sync(0xFFFFFFFFu, w & 0xFFu);
+}
+
 // sum of |byte| over the four int8 of w
 __device__ __forceinline__ int abs_sum4(uint32_t w) { return __dp4a((int)w, (int)(prmt(w, 0u, 0xBA98u) | ONES4), 0); }
 
@@ -83,7 +126,146 @@ __device__ __forceinline__ int norm_inf(uint32_t a0, uint32_t a1) {
     return (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)max(r0, r1));
 }
 
-__global__ void __launch_bounds__(32 * WARPS, 3)
+// range test + int8 packing of sixteen results held as the low 16 bits of d[k' & 3][x]: in [-64, 63] <=> bits 6..15 all equal
+__device__ __forceinline__ void finish4(const uint32_t (&d)[4][4], uint32_t &over, uint32_t (&outw)[4][4], int kq) {
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        const uint32_t w01 = prmt(d[0][x], d[1][x], 0x5410u), w23 = prmt(d[2][x], d[3][x], 0x5410u);
+        over |= ((w01 ^ (w01 + w01)) | (w23 ^ (w23 + w23))) & 0xFF80FF80u;
+        outw[x][kq] = prmt(w01, w23, 0x6420u);
+    }
+}
+
+// everything after the loads, for one game held by one warp.  fm: fragments of C (int8), of A and B with the columns
+// permuted to 2t, 2t+1, 8+2t, 9+2t (int8; the K-slot order of P16's pass 2 and the source of the f16 fragments) and of A
+// with its natural columns 4t..4t+3 (P16's pass 3).
+struct Frags {
+    uint32_t c0, c1, pa0, pa1, pb0, pb1, na0, na1;
+};
+
+template <bool F16, bool STREAM>
+__device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint32_t *__restrict__ src, const Frags &fm, int nA,
+                                                 int nB, int nC, uint32_t *sw, int8_t *__restrict__ out,
+                                                 uint8_t *__restrict__ flag, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t hA[4], hB[4]; // F16: the f16 fragments (rows g | g+8, k = 2t, 2t+1 | 2t+8, 2t+9)
+    if constexpr (F16) {
+        hA[0] = bytes_to_f16(fm.pa0, 0, 1), hA[1] = bytes_to_f16(fm.pa1, 0, 1);
+        hA[2] = bytes_to_f16(fm.pa0, 2, 3), hA[3] = bytes_to_f16(fm.pa1, 2, 3);
+        hB[0] = bytes_to_f16(fm.pb0, 0, 1), hB[1] = bytes_to_f16(fm.pb1, 0, 1);
+        hB[2] = bytes_to_f16(fm.pb0, 2, 3), hB[3] = bytes_to_f16(fm.pb1, 2, 3);
+    }
+    // ---------------- passes 1 and 2, four a at a time; Z leaves packed along a
+    uint32_t ymag = 0; // P16: OR of the magnitudes of the high bytes of Y
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if constexpr (STREAM) {
+            if (q == 1 || q == 2) {
+#pragma unroll
+                for (int x = 0; x < 8; x++) tw[8 * (q + 1) + x] = __ldg(src + (8 * (q + 1) + x) * 32 + lane);
+            }
+        }
+        int zi[4][2][4];   // P16  [a & 3][k' half][2 * (j' half) + (k' & 1)]
+        float zf[4][2][4]; // F16
+#pragma unroll
+        for (int aa = 0; aa < 4; aa++) {
+            const int a = 4 * q + aa;
+            constexpr int C0 = F16 ? MAGIC_BITS : 0;
+            int y0[4] = {C0, C0, C0, C0}, y1[4] = {C0, C0, C0, C0}; // b = 2t, 2t+1 | 8+2t, 9+2t ; rows k' = g | g+8
+            mma_ss(y0, fm.c0, fm.c1, tw[2 * a]);
+            mma_ss(y1, fm.c0, fm.c1, tw[2 * a + 1]);
+#pragma unroll
+            for (int hk = 0; hk < 2; hk++) {
+                if constexpr (F16) {
+                    const uint32_t b0 = pack_f16(__int_as_float(y0[2 * hk]) - MAGIC, __int_as_float(y0[2 * hk + 1]) - MAGIC);
+                    const uint32_t b1 = pack_f16(__int_as_float(y1[2 * hk]) - MAGIC, __int_as_float(y1[2 * hk + 1]) - MAGIC);
+                    zf[aa][hk][0] = zf[aa][hk][1] = zf[aa][hk][2] = zf[aa][hk][3] = 0.f;
+                    mma_f16(zf[aa][hk], hB, b0, b1);
+                } else {
+                    uint32_t lo, hi;
+                    pack_planes(y0[2 * hk], y0[2 * hk + 1], y1[2 * hk], y1[2 * hk + 1], lo, hi);
+                    ymag |= mag4(hi);
+                    mma_planes(zi[aa][hk], fm.pb0, fm.pb1, lo, hi);
+                }
+            }
+        }
+#pragma unroll
+        for (int hj = 0; hj < 2; hj++) {
+            uint32_t w0[4], w1[4]; // position 2 * (k' half) + (k' & 1)  <->  k' = 8 hk + 2t + ek
+#pragma unroll
+            for (int hk = 0; hk < 2; hk++)
+#pragma unroll
+                for (int ek = 0; ek < 2; ek++) {
+                    const int x = 2 * hj + ek;
+                    if constexpr (F16) { // slots a / 2 = 2q, 2q + 1
+                        w0[2 * hk + ek] = pack_f16(zf[0][hk][x], zf[1][hk][x]);
+                        w1[2 * hk + ek] = pack_f16(zf[2][hk][x], zf[3][hk][x]);
+                    } else { // slots q (low bytes), 4 + q (high bytes)
+                        pack_planes(zi[0][hk][x], zi[1][hk][x], zi[2][hk][x], zi[3][hk][x], w0[2 * hk + ek], w1[2 * hk + ek]);
+                    }
+                }
+            uint32_t *dst = sw + (g + 8 * hj) * PJ + 4 * t;
+            *reinterpret_cast<uint4 *>(dst + (F16 ? 2 * q : q) * PQ) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+            *reinterpret_cast<uint4 *>(dst + (F16 ? 2 * q + 1 : 4 + q) * PQ) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        }
+    }
+    if constexpr (!F16) {
+        // exactness guard (see the header): every lane computes the same verdict
+        const long long ybound = 256LL * ((long long)warp_or_bytes(ymag) + 1);
+        if (!(nC <= 255 && ybound * nA * nB <= 32767)) {
+            if (lane == 0) *flag = BASIS_REDO;
+            return;
+        }
+    }
+    __syncwarp();
+
+    // ---------------- pass 3: lane (g,t) now supplies the a of its K slots for column j' = g (+8) and every k'
+    uint32_t over = 0;
+#pragma unroll
+    for (int hj = 0; hj < 2; hj++) {
+        uint32_t r0[16], r1[16]; // slots t and t + 4; index 4s + 2hk + ek  <->  k' = 8 hk + 2s + ek
+        const uint32_t *rsrc = sw + (g + 8 * hj) * PJ + t * PQ;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint4 l4 = *reinterpret_cast<const uint4 *>(rsrc + 4 * s), h4 = *reinterpret_cast<const uint4 *>(rsrc + 4 * PQ + 4 * s);
+            r0[4 * s] = l4.x, r0[4 * s + 1] = l4.y, r0[4 * s + 2] = l4.z, r0[4 * s + 3] = l4.w;
+            r1[4 * s] = h4.x, r1[4 * s + 1] = h4.y, r1[4 * s + 2] = h4.z, r1[4 * s + 3] = h4.w;
+        }
+        uint32_t outw[4][4]; // [2 * (i' half) + (j' & 1)][k' / 4]
+#pragma unroll
+        for (int kq = 0; kq < 4; kq++) {
+            uint32_t d[4][4]; // [k' & 3][2 * (i' half) + (j' & 1)]
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int kp = 4 * kq + e, idx = 4 * ((kp & 7) >> 1) + 2 * (kp >> 3) + (kp & 1);
+                if constexpr (F16) {
+                    float f[4] = {MAGIC, MAGIC, MAGIC, MAGIC};
+                    mma_f16(f, hA, r0[idx], r1[idx]);
+#pragma unroll
+                    for (int x = 0; x < 4; x++) d[e][x] = __float_as_uint(f[x]);
+                } else {
+                    int v[4];
+                    mma_planes(v, fm.na0, fm.na1, r0[idx], r1[idx]);
+#pragma unroll
+                    for (int x = 0; x < 4; x++) d[e][x] = (uint32_t)v[x];
+                }
+            }
+            finish4(d, over, outw, kq);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int ip = g + 8 * (x >> 1), jp = 8 * hj + 2 * t + (x & 1);
+            *reinterpret_cast<uint4 *>(out + ip * 256 + jp * 16) = make_uint4(outw[x][0], outw[x][1], outw[x][2], outw[x][3]);
+        }
+    }
+    const bool bad = __any_sync(0xFFFFFFFFu, over != 0);
+    if (lane == 0) *flag = bad ? (uint8_t)TG_FLAG_RANGE : (uint8_t)0;
+}
+
+// MINB: CTAs per SM the register budget is sized for; STREAM: load the slab words four a at a time (one group ahead)
+// instead of all 32 up front; PATHS: 0 = F16 where its guard holds, else P16 (default), 1 = P16 only (tuning)
+template <int MINB, bool STREAM, int PATHS>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
     basis_mma16_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
                        int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
     extern __shared__ __align__(16) uint32_t s_words[];
@@ -92,102 +274,38 @@ __global__ void __launch_bounds__(32 * WARPS, 3)
     if (n >= N) return;
     uint32_t *sw = s_words + warp * WARP_WORDS;
 
-    // the whole game: 32 coalesced word loads per lane, all in flight before the first MMA
+    // the game: coalesced word loads, in flight before the first MMA
     const uint32_t *src = reinterpret_cast<const uint32_t *>(slab_in + n * 4096);
     uint32_t tw[32];
 #pragma unroll
-    for (int q = 0; q < 32; q++) tw[q] = __ldg(src + q * 32 + lane);
-    // matrix fragments: rows g and g+8, K slots 4t..4t+3
+    for (int q = 0; q < (STREAM && PATHS != 0 ? 16 : 32); q++) tw[q] = __ldg(src + q * 32 + lane);
+    // matrix fragments: rows g and g+8.  Where a pass consumes accumulators directly, the K slots of a lane hold the
+    // contracted indices 2t, 2t+1, 8+2t, 9+2t, so the matrix columns are gathered in that order
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mats + n * mat_stride);
-    const uint32_t fa0 = __ldg(mw + g * 4 + t), fa1 = __ldg(mw + (g + 8) * 4 + t);
-    const uint32_t fc0 = __ldg(mw + 128 + g * 4 + t), fc1 = __ldg(mw + 128 + (g + 8) * 4 + t);
-    const uint32_t selb = (t & 1) ? 0x7632u : 0x5410u; // columns 2t, 2t+1, 8+2t, 9+2t of B
-    const uint32_t fb0 = prmt(__ldg(mw + 64 + g * 4 + (t >> 1)), __ldg(mw + 64 + g * 4 + 2 + (t >> 1)), selb);
-    const uint32_t fb1 = prmt(__ldg(mw + 64 + (g + 8) * 4 + (t >> 1)), __ldg(mw + 64 + (g + 8) * 4 + 2 + (t >> 1)), selb);
-    const int nA = norm_inf(fa0, fa1), nB = norm_inf(fb0, fb1), nC = norm_inf(fc0, fc1);
-
-    // ---------------- passes 1 and 2, four a at a time; Z leaves as byte planes packed along a
-    uint32_t ymag = 0; // OR of the (one's complement) magnitudes of the high bytes of Y
+    const uint32_t sel = (t & 1) ? 0x7632u : 0x5410u;
+    Frags fm;
+    fm.c0 = __ldg(mw + 128 + g * 4 + t), fm.c1 = __ldg(mw + 128 + (g + 8) * 4 + t);
+    fm.na0 = __ldg(mw + g * 4 + t), fm.na1 = __ldg(mw + (g + 8) * 4 + t);
+    fm.pa0 = prmt(__ldg(mw + g * 4 + (t >> 1)), __ldg(mw + g * 4 + 2 + (t >> 1)), sel);
+    fm.pa1 = prmt(__ldg(mw + (g + 8) * 4 + (t >> 1)), __ldg(mw + (g + 8) * 4 + 2 + (t >> 1)), sel);
+    fm.pb0 = prmt(__ldg(mw + 64 + g * 4 + (t >> 1)), __ldg(mw + 64 + g * 4 + 2 + (t >> 1)), sel);
+    fm.pb1 = prmt(__ldg(mw + 64 + (g + 8) * 4 + (t >> 1)), __ldg(mw + 64 + (g + 8) * 4 + 2 + (t >> 1)), sel);
+    const int nA = norm_inf(fm.pa0, fm.pa1), nB = norm_inf(fm.pb0, fm.pb1), nC = norm_inf(fm.c0, fm.c1);
+    int8_t *out = slab_out + n * 4096;
+    if constexpr (PATHS == 0) {
+        // the a-priori bound needs max|T|: the whole game is read first
+        uint32_t tm = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int z[4][2][4]; // [a & 3][k' half][2 * (j' half) + (k' & 1)]
-#pragma unroll
-        for (int aa = 0; aa < 4; aa++) {
-            const int a = 4 * q + aa;
-            int y0[4] = {0, 0, 0, 0}, y1[4] = {0, 0, 0, 0}; // b = 2t, 2t+1 | 8+2t, 9+2t ; rows k' = g | g+8
-            mma_ss(y0, fc0, fc1, tw[2 * a]);
-            mma_ss(y1, fc0, fc1, tw[2 * a + 1]);
-#pragma unroll
-            for (int hk = 0; hk < 2; hk++) {
-                uint32_t lo, hi;
-                pack_planes(y0[2 * hk], y0[2 * hk + 1], y1[2 * hk], y1[2 * hk + 1], lo, hi);
-                ymag |= hi ^ prmt(hi, 0u, 0xBA98u);
-                mma_planes(z[aa][hk], fb0, fb1, lo, hi);
-            }
+        for (int q = 0; q < 32; q++) tm |= mag4(tw[q]);
+        const long long yb = ((long long)warp_or_bytes(tm) + 1) * nC, zb = yb * nB;
+        if (yb <= 2048 && zb <= 2048 && zb * nA <= 32767) {
+            basis_mma16_game<true, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
+            return;
         }
-#pragma unroll
-        for (int hj = 0; hj < 2; hj++) {
-            uint32_t lo[4], hi[4]; // position 2 * (k' half) + (k' & 1)  <->  k' = 8 hk + 2t + ek
-#pragma unroll
-            for (int hk = 0; hk < 2; hk++)
-#pragma unroll
-                for (int ek = 0; ek < 2; ek++)
-                    pack_planes(z[0][hk][2 * hj + ek], z[1][hk][2 * hj + ek], z[2][hk][2 * hj + ek], z[3][hk][2 * hj + ek],
-                                lo[2 * hk + ek], hi[2 * hk + ek]);
-            uint32_t *dst = sw + (g + 8 * hj) * PJ + q * PQ + 4 * t;
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4 *>(dst + PP) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        }
+        basis_mma16_game<false, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
+    } else {
+        basis_mma16_game<false, STREAM>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
     }
-    // exactness guard (see the header): every lane computes the same verdict
-    ymag |= ymag >> 16;
-    ymag |= ymag >> 8;
-    const long long ybound = 256LL * ((long long)__reduce_or_sync(0xFFFFFFFFu, ymag & 0xFFu) + 1);
-    if (!(nC <= 255 && ybound * nA * nB <= 32767)) {
-        if (lane == 0) flags[n] = BASIS_REDO;
-        return;
-    }
-    __syncwarp();
-
-    // ---------------- pass 3: lane (g,t) now supplies a = 4t..4t+3 of column j' = g (+8) for every k'
-    uint32_t over = 0;
-#pragma unroll
-    for (int hj = 0; hj < 2; hj++) {
-        uint32_t rl[16], rh[16]; // index 4s + 2hk + ek  <->  k' = 8 hk + 2s + ek
-        const uint32_t *rsrc = sw + (g + 8 * hj) * PJ + t * PQ;
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            const uint4 l4 = *reinterpret_cast<const uint4 *>(rsrc + 4 * s), h4 = *reinterpret_cast<const uint4 *>(rsrc + PP + 4 * s);
-            rl[4 * s] = l4.x, rl[4 * s + 1] = l4.y, rl[4 * s + 2] = l4.z, rl[4 * s + 3] = l4.w;
-            rh[4 * s] = h4.x, rh[4 * s + 1] = h4.y, rh[4 * s + 2] = h4.z, rh[4 * s + 3] = h4.w;
-        }
-        uint32_t outw[4][4]; // [2 * (i' half) + (j' & 1)][k' / 4]
-#pragma unroll
-        for (int kq = 0; kq < 4; kq++) {
-            int d[4][4]; // [k' & 3][2 * (i' half) + (j' & 1)]
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int kp = 4 * kq + e, idx = 4 * ((kp & 7) >> 1) + 2 * (kp >> 3) + (kp & 1);
-                mma_planes(d[e], fa0, fa1, rl[idx], rh[idx]);
-            }
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                // 16-bit lanes: in [-64, 63]  <=>  bits 6..15 all equal
-                const uint32_t w01 = prmt((uint32_t)d[0][x], (uint32_t)d[1][x], 0x5410u);
-                const uint32_t w23 = prmt((uint32_t)d[2][x], (uint32_t)d[3][x], 0x5410u);
-                over |= ((w01 ^ (w01 + w01)) | (w23 ^ (w23 + w23))) & 0xFF80FF80u;
-                outw[x][kq] = prmt(w01, w23, 0x6420u);
-            }
-        }
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int ip = g + 8 * (x >> 1), jp = 8 * hj + 2 * t + (x & 1);
-            *reinterpret_cast<uint4 *>(slab_out + n * 4096 + ip * 256 + jp * 16) =
-                make_uint4(outw[x][0], outw[x][1], outw[x][2], outw[x][3]);
-        }
-    }
-    const bool bad = __any_sync(0xFFFFFFFFu, over != 0);
-    if (lane == 0) flags[n] = bad ? (uint8_t)TG_FLAG_RANGE : (uint8_t)0;
 }
 
 } // namespace
@@ -195,8 +313,22 @@ __global__ void __launch_bounds__(32 * WARPS, 3)
 int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, int8_t *slab_out, uint8_t *flags,
                        long long N, cudaStream_t st) {
     constexpr int SMEM = WARPS * WARP_WORDS * 4;
-    TG_CUDA(cudaFuncSetAttribute(basis_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    basis_mma16_kernel<<<(unsigned)((N + WARPS - 1) / WARPS), 32 * WARPS, SMEM, st>>>(slab_in, mats, mat_stride, slab_out, flags, N);
+    static const int variant = getenv("TG_BASIS_VARIANT") ? atoi(getenv("TG_BASIS_VARIANT")) : 0; // tuning sweeps only
+    const unsigned grid = (unsigned)((N + WARPS - 1) / WARPS);
+#define TG_MMA16_LAUNCH(MINB, STREAM, PATHS)                                                                           \
+    {                                                                                                                  \
+        auto kern = basis_mma16_kernel<MINB, STREAM, PATHS>;                                                                \
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                        \
+        kern<<<grid, 32 * WARPS, SMEM, st>>>(slab_in, mats, mat_stride, slab_out, flags, N);                           \
+    }
+    switch (variant) {
+    case 2: TG_MMA16_LAUNCH(4, true, 1) break;  // 16-bit planes only
+    case 3: TG_MMA16_LAUNCH(3, false, 0) break;
+    case 5: TG_MMA16_LAUNCH(5, false, 0) break;
+    default: TG_MMA16_LAUNCH(4, false, 0) break;
+    }
+#undef TG_MMA16_LAUNCH
+    TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
 

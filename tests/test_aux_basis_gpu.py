@@ -168,21 +168,26 @@ def test_change_of_basis_tensor_core_path_16(env):
     T[7] = 127
     T[8] = 0
     m = np.zeros((N, 3, S, S), dtype=np.int64)
-    uni = orc.sample_unimodular(3, 0, N, S, 0.03)
+    uni = orc.sample_unimodular(3, 0, N, S, 0.03)  # small norms: the 12-bit K = 32 path
+    uni2 = orc.sample_unimodular(4, 0, N, S, 0.12)  # larger norms: the 16-bit path (or, beyond its guard, the exact kernel)
     for n in range(N):
         kind = n % 6
         if kind == 0:
             m[n] = np.eye(S, dtype=np.int64)
         elif kind == 1:
             m[n] = np.stack([np.eye(S, dtype=np.int64)[rng.permutation(S)] * rng.choice([-1, 1], (S, 1)) for _ in range(3)])
-        elif kind in (2, 3):
+        elif kind == 2:
             m[n] = uni[n]
+        elif kind == 3:
+            m[n] = uni2[n]
         elif kind == 4:
             m[n] = np.eye(S, dtype=np.int64) + rng.integers(-1, 2, (3, S, S)) * (rng.random((3, S, S)) < 0.04)
         else:
             m[n] = rng.integers(-3, 4, (3, S, S)) * (rng.random((3, S, S)) < 0.3)
     m[9, 2] = -128  # ||C||inf far beyond the guard
     m[10, 0, 3] = 127
+    m[12, 1, 5, 5] = 8  # an entry of B too large for the 12-bit path's [M | 16 M] fragment
+    m[18, 0, 2, 2] = -8
     slab = torch.from_numpy(dense_to_slab(T)).cuda()
     out, flags = env.change_of_basis(slab, torch.from_numpy(m.astype(np.int8)).cuda(), S)
     want = np.einsum("nia,njb,nkc,nabc->nijk", m[:, 0], m[:, 1], m[:, 2], T)
