@@ -170,6 +170,25 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, bar
                              "env_steps_per_sec": B4 / ms_step * 1e3,
                              "step_hbm_frac": B4 * ALGO_BYTES[4] / (ms_step * 1e-3) / 1e9 / peak}
         del t4, s4, o4
+    if S == 9:
+        # BASELINE.json configs[2]: 16x16x16 demos (rank <= 49) followed by the change-of-basis augmentation, one
+        # (A, B, C) triple per demo -- the one contraction that runs on the tensor cores (csrc/tg_basis_mma.cu)
+        S16, R16, B16 = 16, 49, 1 << 17
+        t16, s16, _ = env.make_synthetic_demos(B16, R16, S16, values, probs, shift, seed=3, device=dev)
+        ms = _time_ms(lambda: env.make_synthetic_demos(B16, R16, S16, values, probs, shift, seed=3, device=dev, tape=t16, slab=s16), 3, torch)
+        algo16 = S16 ** 3 + R16 * 3 * S16
+        m16 = env.sample_unimodular(B16, S16, seed=3, p_nonzero=0.03, device=dev)
+        ms_cb = _time_ms(lambda: env.change_of_basis(s16, m16, S16), 5, torch)
+        ms_cbf = _time_ms(lambda: env.change_of_basis(s16, m16, S16, tape=t16, shift=shift, shift_out=100), 3, torch)
+        moved16 = 2 * S16 ** 3 + 3 * S16 * S16
+        out["size_16x16x16"] = {"games": B16, "R": R16, "synthetic_demos_per_sec": B16 / ms * 1e3,
+                                "demo_hbm_frac": B16 * algo16 / (ms * 1e-3) / 1e9 / peak,
+                                "change_of_basis_games_per_sec": B16 / ms_cb * 1e3, "change_of_basis_ms": ms_cb,
+                                "change_of_basis_hbm_frac": B16 * moved16 / (ms_cb * 1e-3) / 1e9 / peak,
+                                "change_of_basis_hbm_frac_survey_bytes": B16 * (moved16 + S16 ** 3) / (ms_cb * 1e-3) / 1e9 / peak,
+                                "change_of_basis_with_factors_games_per_sec": B16 / ms_cbf * 1e3,
+                                "kernel": "basis_mma16_kernel (mma.sync int8 + f16, one warp per game)"}
+        del t16, s16, m16
     if world > 1:  # demo all-gather timed as its own phase (NVLink-bound)
         from mat_mul_b200 import dist as tgd
 

@@ -263,8 +263,9 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
 }
 
 // MINB: CTAs per SM the register budget is sized for; STREAM: load the slab words four a at a time (one group ahead)
-// instead of all 32 up front; PATHS: 0 = F16 where its guard holds, else P16 (default), 1 = P16 only (tuning)
-template <int MINB, bool STREAM, int PATHS>
+// instead of all 32 up front; PATHS: 0 = F16 where its guard holds, else P16 (default), 1 = P16 only (tuning);
+// PREFETCH: L2 prefetch distance in CTAs per SM (0 = none)
+template <int MINB, bool STREAM, int PATHS, int PREFETCH>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
     basis_mma16_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
                        int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
@@ -279,6 +280,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB)
     uint32_t tw[32];
 #pragma unroll
     for (int q = 0; q < (STREAM && PATHS != 0 ? 16 : 32); q++) tw[q] = __ldg(src + q * 32 + lane);
+    // pull the game a later wave of CTAs will work on (and its matrices) into L2: one line per lane
+    if constexpr (PREFETCH > 0) {
+        const long long np = n + (long long)PREFETCH * 148 * WARPS;
+        if (np < N) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(slab_in + np * 4096 + lane * 128));
+            if (lane < 6 && mat_stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(mats + np * mat_stride + lane * 128));
+        }
+    }
     // matrix fragments: rows g and g+8.  Where a pass consumes accumulators directly, the K slots of a lane hold the
     // contracted indices 2t, 2t+1, 8+2t, 9+2t, so the matrix columns are gathered in that order
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mats + n * mat_stride);
@@ -315,17 +324,16 @@ int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_
     constexpr int SMEM = WARPS * WARP_WORDS * 4;
     static const int variant = getenv("TG_BASIS_VARIANT") ? atoi(getenv("TG_BASIS_VARIANT")) : 0; // tuning sweeps only
     const unsigned grid = (unsigned)((N + WARPS - 1) / WARPS);
-#define TG_MMA16_LAUNCH(MINB, STREAM, PATHS)                                                                           \
+#define TG_MMA16_LAUNCH(MINB, STREAM, PATHS, PF)                                                                        \
     {                                                                                                                  \
-        auto kern = basis_mma16_kernel<MINB, STREAM, PATHS>;                                                                \
+        auto kern = basis_mma16_kernel<MINB, STREAM, PATHS, PF>;                                                                \
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                        \
         kern<<<grid, 32 * WARPS, SMEM, st>>>(slab_in, mats, mat_stride, slab_out, flags, N);                           \
     }
     switch (variant) {
-    case 2: TG_MMA16_LAUNCH(4, true, 1) break;  // 16-bit planes only
-    case 3: TG_MMA16_LAUNCH(3, false, 0) break;
-    case 5: TG_MMA16_LAUNCH(5, false, 0) break;
-    default: TG_MMA16_LAUNCH(4, false, 0) break;
+    case 2: TG_MMA16_LAUNCH(4, true, 1, 0) break;  // 16-bit planes only
+    case 3: TG_MMA16_LAUNCH(4, false, 0, 0) break; // no L2 prefetch
+    default: TG_MMA16_LAUNCH(4, false, 0, 4) break; // measured best (profiles/README.md): prefetch one wave of CTAs ahead
     }
 #undef TG_MMA16_LAUNCH
     TG_CUDA(cudaGetLastError());
