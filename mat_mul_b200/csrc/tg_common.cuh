@@ -42,6 +42,11 @@ constexpr uint8_t BASIS_REDO = 0x80;
 int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, int8_t *slab_out, uint8_t *flags,
                        long long N, cudaStream_t st);
 
+// tg_demo_mma.cu: sum of the R rank-1 terms of 16x16x16 action lists, one warp per demo on mma.sync f16 (R <= 64)
+bool demo_acc16_mma_applies(int R);
+int launch_demo_acc16_mma(const uint8_t *tape, long long tape_step_stride, long long N, int R, int shift, int8_t *slab,
+                          uint8_t *flags, int or_flags, cudaStream_t st);
+
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA 1-D)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

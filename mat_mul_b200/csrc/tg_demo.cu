@@ -180,7 +180,9 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
     return (int)prmt(w, 0u, sel);
 }
 
-template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD>
+// ACC = false: sample only (phase A writes the tape; no records, no phases B and C) -- the 16x16x16 targets are then
+// summed on the tensor cores by tg_demo_mma.cu
+template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD, bool ACC = true>
 __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 5 : 4))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     uint8_t *s_rec = smem;  // [TG][R][REC] accumulate records (phases A, B) ...
     // ... then (OVERLAY) the slab tile [TG][PITCH] (end of B, C) in the same bytes, else a region of its own
     uint8_t *s_slab = C::OVERLAY ? smem : smem + C::rec_region(R);
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + C::main_bytes(R)); // [TG]
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (ACC ? C::main_bytes(R) : 0)); // [TG]
     uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
     uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16)
 
@@ -237,7 +239,8 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
 #pragma unroll
                 for (int w = 0; w < G::TP / 16; w++)
                     dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
-                emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+                if constexpr (ACC)
+                    emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
             }
             return ok;
         };
@@ -324,6 +327,11 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
         }
     }
     __syncthreads();
+    if constexpr (!ACC) {
+        if (flags)
+            for (int gg = tid; gg < ng; gg += NT) flags[g0 + gg] = (uint8_t)s_flag[gg];
+        return;
+    }
 
     // ---------------- B. accumulate the R rank-1 terms in registers
     constexpr int KW = C::KW;
@@ -470,6 +478,22 @@ static int launch_demo(unsigned long long first, long long N, int R, int shift, 
     return TG_OK;
 }
 
+// 16x16x16 sampling only (32-demo tiles: no records in shared memory, so the tile size only has to amortise the retry tail)
+template <int NTHR>
+static int launch_sample16(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
+                           uint8_t *tape, long long stride, uint8_t *flags, cudaStream_t st) {
+    using C = DemoCfg<16, 128, 4>;
+    const int smem = C::TG * 4 + 16 + 2 * 128 * 4;
+    if (R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
+    const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
+    const long long grid = (N + C::TG - 1) / C::TG;
+    if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+    demo_kernel<16, 128, 4, true, NTHR, false, false><<<(int)grid, 128, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape,
+                                                                                 stride, nullptr, flags);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
 template <bool SAMPLE, int NTHR>
 static int dispatch_demo(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
                          int max_tries, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
@@ -553,6 +577,16 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
         cat.rk[r][1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // 16x16x16, R <= 64: sample the tape, then sum the targets on the tensor cores (tg_demo_mma.cu); TG_DEMO_MMA=0 keeps
+    // the fused packed-IMAD kernel (A/B timing only)
+    static const int use_mma = getenv("TG_DEMO_MMA") ? atoi(getenv("TG_DEMO_MMA")) : 1;
+    if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R)) {
+        const int rc = n_values <= 3   ? tg::launch_sample16<2>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, flags, st)
+                       : n_values <= 5 ? tg::launch_sample16<4>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, flags, st)
+                                       : tg::launch_sample16<7>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, flags, st);
+        if (rc != TG_OK) return rc;
+        return tg::launch_demo_acc16_mma(tape, tape_step_stride, N, R, shift, slab, flags, 1, st);
+    }
     if (n_values <= 3)
         return tg::dispatch_demo<true, 2>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
     if (n_values <= 5)
@@ -566,6 +600,10 @@ int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N,
     if (N == 0) return TG_OK;
     if (!tape || !slab) return TG_E_ARG;
     if (((uintptr_t)tape | (uintptr_t)slab | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
+    // 16x16x16: tensor cores (tg_demo_mma.cu); TG_DEMO_MMA=0 keeps the packed-IMAD kernel (A/B timing only)
+    static const int use_mma = getenv("TG_DEMO_MMA") ? atoi(getenv("TG_DEMO_MMA")) : 1;
+    if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R))
+        return tg::launch_demo_acc16_mma(tape, tape_step_stride, N, R, shift, slab, flags, 0, (cudaStream_t)stream);
     tg::Categorical cat = {};
     return tg::dispatch_demo<false, 2>(0, N, R, S, shift, cat, 1, const_cast<uint8_t *>(tape), tape_step_stride, slab, flags,
                                        (cudaStream_t)stream);
