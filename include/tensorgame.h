@@ -132,10 +132,11 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
  * list (utils.py:40-53 uvw_to_demo, utils.py:232, datasets.py:141). */
 int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,
                        uint8_t *flags, void *stream);
-/* The same sum on the 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM): S = 16 and
- * R <= 64 only (TG_E_ARG otherwise).  tg_demo_accumulate and tg_demo_gen_philox take this path by themselves when
- * it applies; the separate entry point exists for tests and profiling.  Entries beyond int8 are stored saturated
- * (and flagged) instead of wrapped. */
+/* For S = 16 and R <= 64 tg_demo_accumulate and tg_demo_gen_philox sum the targets on the tensor cores
+ * (mma.sync f16, exact integer arithmetic; csrc/tg_demo_mma.cu) -- same results.
+ * tg_demo_accumulate_tc: the same sum with tcgen05.mma kind::i8 (int32 accumulators in TMEM), an experimental entry
+ * point kept for tests and profiling: S = 16 and R <= 64 only (TG_E_ARG otherwise); entries beyond int8 are stored
+ * saturated (and flagged) instead of wrapped. */
 int tg_demo_accumulate_tc(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,
                           uint8_t *flags, void *stream);
 

@@ -17,7 +17,7 @@ HEADER = PKG.parent / "include" / "tensorgame.h"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "--threads", "0",
 ]
 
 TG_OK = 0

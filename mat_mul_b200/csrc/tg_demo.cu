@@ -31,6 +31,7 @@
 //   C. the slab tile leaves through one TMA bulk store.
 #include <cstdlib>
 
+#include "tg_demo_mma.cuh"
 #include "tg_step.cuh"
 
 namespace tg {
@@ -180,9 +181,11 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
     return (int)prmt(w, 0u, sel);
 }
 
-// ACC = false: sample only (phase A writes the tape; no records, no phases B and C) -- the 16x16x16 targets are then
-// summed on the tensor cores by tg_demo_mma.cu
-template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD, bool ACC = true>
+// MMA = 0: phases A, B, C as described above.  MMA = -1: sample only (phase A writes the tape, nothing else).
+// MMA = KS > 0 (16x16x16, R <= 16 KS): phase A also leaves the raw 48-byte action records in shared memory and every warp
+// then sums the targets of its demos on the tensor cores (tg_demo_mma.cuh) -- CTAs of one SM are in different phases, so
+// the sampler's integer work and the MMAs overlap.
+template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD, int MMA = 0>
 __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 5 : 4))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     uint8_t *s_rec = smem;  // [TG][R][REC] accumulate records (phases A, B) ...
     // ... then (OVERLAY) the slab tile [TG][PITCH] (end of B, C) in the same bytes, else a region of its own
     uint8_t *s_slab = C::OVERLAY ? smem : smem + C::rec_region(R);
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (ACC ? C::main_bytes(R) : 0)); // [TG]
+    constexpr int MMA_SCRATCH = MMA > 0 ? (NT / 32) * acc16::WARP_WORDS * 4 : 0; // per-warp H and U2 tables
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (MMA == 0 ? C::main_bytes(R) : MMA > 0 ? C::rec_region(R) + MMA_SCRATCH : 0)); // [TG]
     uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
     uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16)
 
@@ -239,8 +243,14 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
 #pragma unroll
                 for (int w = 0; w < G::TP / 16; w++)
                     dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
-                if constexpr (ACC)
+                if constexpr (MMA == 0) {
                     emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+                } else if constexpr (MMA > 0) {
+                    uint4 *rdst = reinterpret_cast<uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
+#pragma unroll
+                    for (int w = 0; w < G::TP / 16; w++)
+                        rdst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
+                }
             }
             return ok;
         };
@@ -327,7 +337,31 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
         }
     }
     __syncthreads();
-    if constexpr (!ACC) {
+    if constexpr (MMA != 0) {
+        if constexpr (MMA > 0) {
+            static_assert(MMA <= 0 || (S == 16 && G::TP == 48), "tensor-core accumulation: 16x16x16 only");
+            const int warp = tid >> 5;
+            uint32_t *sH = reinterpret_cast<uint32_t *>(smem + C::rec_region(R)) + warp * acc16::WARP_WORDS, *sU = sH + acc16::H_WORDS;
+            for (int g = warp; g < ng; g += NT / 32) {
+#pragma unroll
+                for (int pass = 0; pass < (MMA + 1) / 2; pass++) {
+                    const int r = 32 * pass + lane;
+                    if (r < 16 * MMA) {
+                        const uint32_t z = (uint32_t)shift * ONES4; // coefficient 0
+                        uint4 raw[3] = {make_uint4(z, z, z, z), make_uint4(z, z, z, z), make_uint4(z, z, z, z)};
+                        if (r < R) {
+                            const uint4 *src = reinterpret_cast<const uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
+                            raw[0] = src[0], raw[1] = src[1], raw[2] = src[2];
+                        }
+                        acc16::record_to_halves(raw, shift, sH + r * acc16::HP);
+                    }
+                }
+                __syncwarp();
+                const bool bad = acc16::gemms_from_halves<MMA>(sH, sU, slab + (g0 + g) * G::GP, lane);
+                if (bad && lane == 0) s_flag[g] |= (uint32_t)TG_FLAG_RANGE; // this warp is the only writer of s_flag[g] now
+            }
+            __syncthreads();
+        }
         if (flags)
             for (int gg = tid; gg < ng; gg += NT) flags[g0 + gg] = (uint8_t)s_flag[gg];
         return;
@@ -478,20 +512,34 @@ static int launch_demo(unsigned long long first, long long N, int R, int shift, 
     return TG_OK;
 }
 
-// 16x16x16 sampling only (32-demo tiles: no records in shared memory, so the tile size only has to amortise the retry tail)
-template <int NTHR>
-static int launch_sample16(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
-                           uint8_t *tape, long long stride, uint8_t *flags, cudaStream_t st) {
-    using C = DemoCfg<16, 128, 4>;
-    const int smem = C::TG * 4 + 16 + 2 * 128 * 4;
-    if (R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
+// 16x16x16, R <= 64: sampling fused with the tensor-core accumulation (KS = K-steps of 16 actions), or sampling only
+template <int NTHR, int NPASS, int MMA>
+static int launch_demo16_mma(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
+                             uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
+    using C = DemoCfg<16, 128, NPASS>;
+    const int smem = (MMA > 0 ? C::rec_region(R) + 4 * acc16::WARP_WORDS * 4 : 0) + C::TG * 4 + 16 + 2 * 128 * 4;
+    if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
-    demo_kernel<16, 128, 4, true, NTHR, false, false><<<(int)grid, 128, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape,
-                                                                                 stride, nullptr, flags);
+    auto kern = demo_kernel<16, 128, NPASS, true, NTHR, false, MMA>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(int)grid, 128, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
+}
+
+template <int NTHR>
+static int dispatch_demo16_mma(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
+                               uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
+    static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+    if (variant == 9) { // two kernels: sample, then sum from the tape
+        const int rc = launch_demo16_mma<NTHR, 4, -1>(first, N, R, shift, cat, max_tries, tape, stride, nullptr, flags, st);
+        return rc != TG_OK ? rc : launch_demo_acc16_mma(tape, stride, N, R, shift, slab, flags, 1, st);
+    }
+    if (R <= 32) return launch_demo16_mma<NTHR, 2, 2>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    if (variant == 8) return launch_demo16_mma<NTHR, 1, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    return launch_demo16_mma<NTHR, 2, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
 }
 
 template <bool SAMPLE, int NTHR>
@@ -577,15 +625,13 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
         cat.rk[r][1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    // 16x16x16, R <= 64: sample the tape, then sum the targets on the tensor cores (tg_demo_mma.cu); TG_DEMO_MMA=0 keeps
-    // the fused packed-IMAD kernel (A/B timing only)
+    // 16x16x16, R <= 64: the targets are summed on the tensor cores (tg_demo_mma.cuh) inside the sampling kernel;
+    // TG_DEMO_MMA=0 keeps the packed-IMAD accumulation (A/B timing only)
     static const int use_mma = getenv("TG_DEMO_MMA") ? atoi(getenv("TG_DEMO_MMA")) : 1;
     if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R)) {
-        const int rc = n_values <= 3   ? tg::launch_sample16<2>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, flags, st)
-                       : n_values <= 5 ? tg::launch_sample16<4>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, flags, st)
-                                       : tg::launch_sample16<7>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, flags, st);
-        if (rc != TG_OK) return rc;
-        return tg::launch_demo_acc16_mma(tape, tape_step_stride, N, R, shift, slab, flags, 1, st);
+        if (n_values <= 3) return tg::dispatch_demo16_mma<2>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
+        if (n_values <= 5) return tg::dispatch_demo16_mma<4>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
+        return tg::dispatch_demo16_mma<7>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
     }
     if (n_values <= 3)
         return tg::dispatch_demo<true, 2>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
