@@ -27,7 +27,10 @@ __device__ __forceinline__ void vw_bytes(const uint8_t *tok, const Lane<S> &L, i
 
 // PACK16: the head is accumulated two entries per 32-bit word (16-bit lanes in integer form, one IMAD per two
 // entries, half the registers -> more samples in flight); the host takes this path when R * cmax^3 + 128 fits int16.
-template <int S, bool PACK16>
+// STAGE: the CTA first copies the action records a .. R-1 of all its samples into shared memory, every load in flight at
+// once (the step-major tape puts each record of a demo in a different DRAM page; read one after the other inside the
+// replay loop they serialise into R - a round trips per sample, which is what bounded this kernel).
+template <int S, bool PACK16, bool STAGE>
 __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
     demo_sample_kernel(const uint8_t *__restrict__ tape, long long tape_step_stride,
                                    const int8_t *__restrict__ slab, long long N, int R, int dim_t, int replay_shift,
@@ -35,8 +38,27 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
                                    float *__restrict__ scalars, long long *__restrict__ actions,
                                    float *__restrict__ rewards) {
     using G = Geo<S>;
+    extern __shared__ __align__(16) uint8_t s_tok[]; // STAGE: [samples of the CTA][R][TP]
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long b = t / G::WR;
+    const long long b0 = (blockIdx.x * (long long)blockDim.x) / G::WR; // first sample this CTA touches
+    if constexpr (STAGE) {
+        constexpr int SLOTS = (128 + G::WR - 1) / G::WR + 1;
+        const int nslots = (int)min((long long)SLOTS, nb - b0);
+        for (int item = threadIdx.x; item < nslots * R; item += 128) {
+            const int sl = item / R, j = item - sl * R;
+            const long long id2 = idx[b0 + sl];
+            const long long demo2 = id2 / R;
+            const int a2 = (int)(id2 - demo2 * R);
+            if (demo2 >= 0 && demo2 < N && j >= a2) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(tape + (size_t)j * tape_step_stride + demo2 * G::TP);
+                uint4 *dst = reinterpret_cast<uint4 *>(s_tok + ((size_t)sl * R + j) * G::TP);
+#pragma unroll
+                for (int w = 0; w < G::TP / 16; w++) dst[w] = __ldg(src + w);
+            }
+        }
+        __syncthreads();
+    }
     if (b >= nb) return;
     Lane<S> L;
     L.init((int)(t % G::WR));
@@ -44,7 +66,8 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
     const long long demo = id / R;
     const int a = (int)(id - demo * R);
     if (demo < 0 || demo >= N) return;
-    const uint8_t *tk = tape + demo * G::TP;
+    const uint8_t *tk = STAGE ? s_tok + (size_t)(b - b0) * R * G::TP : tape + demo * G::TP;
+    if constexpr (STAGE) tape_step_stride = G::TP;
     // head
     float *st = states + b * (long long)dim_t * G::S3;
     const int8_t *tg = slab + demo * G::GP + 4 * L.c;
@@ -256,6 +279,36 @@ __global__ void __launch_bounds__(256) state_key_kernel(const int8_t *__restrict
     default: return TG_E_ARG; \
     }
 
+namespace tg {
+
+template <int S, bool P16, bool STG>
+static int launch_demo_sample_variant(unsigned grid, size_t smem, const uint8_t *tape, long long tape_step_stride, const int8_t *slab,
+                                      long long N, int R, int dim_t, int replay_shift, const long long *idx, long long nb,
+                                      float *states, float *scalars, long long *actions, float *rewards, cudaStream_t st) {
+    auto kern = demo_sample_kernel<S, P16, STG>;
+    if (STG) TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, STG ? smem : 0, st>>>(tape, tape_step_stride, slab, N, R, dim_t, replay_shift, idx, nb, states, scalars,
+                                            actions, rewards);
+    return TG_OK;
+}
+
+template <int S>
+static int launch_demo_sample(const uint8_t *tape, long long tape_step_stride, const int8_t *slab, long long N, int R, int dim_t,
+                              int replay_shift, const long long *idx, long long nb, float *states, float *scalars,
+                              long long *actions, float *rewards, bool pack16, cudaStream_t st) {
+    using G = Geo<S>;
+    const unsigned grid = (unsigned)((nb * G::WR + 127) / 128);
+    // staging needs 16-byte aligned records and room for the records of every sample a CTA touches
+    const long long smem = ((128 + G::WR - 1) / G::WR + 1) * (long long)R * G::TP;
+    const bool stage = (((uintptr_t)tape | (uintptr_t)tape_step_stride) & 15) == 0 && smem <= 64 * 1024;
+#define TG_ARGS grid, (size_t)smem, tape, tape_step_stride, slab, N, R, dim_t, replay_shift, idx, nb, states, scalars, actions, rewards, st
+    if (pack16) return stage ? launch_demo_sample_variant<S, true, true>(TG_ARGS) : launch_demo_sample_variant<S, true, false>(TG_ARGS);
+    return stage ? launch_demo_sample_variant<S, false, true>(TG_ARGS) : launch_demo_sample_variant<S, false, false>(TG_ARGS);
+#undef TG_ARGS
+}
+
+} // namespace tg
+
 extern "C" {
 
 int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *slab, int64_t N, int R, int S, int dim_t,
@@ -270,15 +323,9 @@ int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *
     const long long cmax = replay_shift > 8 - replay_shift ? replay_shift : 8 - replay_shift;
     const bool pack16 = replay_shift >= 0 && replay_shift <= 8 && 127 + (long long)R * cmax * cmax * cmax <= 32767;
     TG_SWITCH_S(S, {
-        const long long threads = nb * tg::Geo<kS>::WR;
-        if (pack16)
-            tg::demo_sample_kernel<kS, true><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb, states, scalars,
-                (long long *)actions, rewards);
-        else
-            tg::demo_sample_kernel<kS, false><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb, states, scalars,
-                (long long *)actions, rewards);
+        const int rc = tg::launch_demo_sample<kS>(tape, tape_step_stride, slab, N, R, dim_t, replay_shift, (const long long *)idx, nb,
+                                                  states, scalars, (long long *)actions, rewards, pack16, st);
+        if (rc != TG_OK) return rc;
     });
     TG_CUDA(cudaGetLastError());
     return TG_OK;
