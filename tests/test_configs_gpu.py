@@ -99,3 +99,33 @@ def test_config5_rollout_sweep_fused_equals_per_step_launches(env, B):
     # the un-frozen replay (tg_replay) applies all K actions and ends in the same place
     rep, rf, rn = env.replay(slab, tapeK, S, shift)
     assert torch.equal(rep, fused)
+
+
+def test_full_size_16_tensor_core_paths_by_invariants(env):
+    """BASELINE.json configs[2] at scale, through size-independent properties (no oracle at this size):
+    (1) 2^16 generated 16x16x16 demos of rank 49 (targets summed on the tensor cores) replay to the zero tensor;
+    (2) accumulate(tape) rebuilds the generated targets bit for bit;
+    (3) change of basis by random signed permutation matrices, then by their transposes, is the identity, keeps the
+        multiset of entries of every game, and the sum of squares is a checksum of checksums."""
+    S, R, shift, N = 16, 49, 2, 1 << 16
+    tape, slab, flags = env.make_synthetic_demos(N, R, S, V5, P5, shift, seed=2024)
+    assert not (flags & 8).any()
+    inr = (flags & 4) == 0  # demos whose target stays in the int8 guaranteed zone
+    assert int(inr.sum()) > N * 0.99
+    out, f, nnz, steps = env.rollout(slab, tape.flip(0).contiguous(), S, shift)
+    assert not out[inr].any() and bool((f[inr] & 1).all()) and not nnz[inr].any()
+    slab2, flags2 = env.accumulate_demos(tape, S, shift)
+    assert torch.equal(slab2, slab) and torch.equal(flags2 & 4, flags & 4)
+    # (3)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    perm = torch.rand((N, 3, S), device="cuda", generator=g).argsort(dim=-1)  # one permutation per game and mode
+    sign = (torch.randint(0, 2, (N, 3, S), device="cuda", generator=g) * 2 - 1).to(torch.int8)
+    mats = torch.zeros((N, 3, S, S), dtype=torch.int8, device="cuda")
+    mats.scatter_(3, perm.unsqueeze(-1), sign.unsqueeze(-1))
+    t1, f1 = env.change_of_basis(slab, mats, S)
+    back, f2 = env.change_of_basis(t1, mats.transpose(2, 3).contiguous(), S)
+    assert torch.equal(back, slab)
+    assert torch.equal(f1 & 4, flags & 4) and torch.equal(f2 & 4, flags & 4) and not ((f1 | f2) & 0x80).any()
+    sq = lambda x: (x.to(torch.int32) ** 2).sum(dim=1)
+    assert torch.equal(sq(t1), sq(slab))
+    assert torch.equal(t1.to(torch.int16).abs().sort(dim=1).values[:: 257], slab.to(torch.int16).abs().sort(dim=1).values[:: 257])
