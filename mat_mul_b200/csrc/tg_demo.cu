@@ -513,18 +513,18 @@ static int launch_demo(unsigned long long first, long long N, int R, int shift, 
 }
 
 // 16x16x16, R <= 64: sampling fused with the tensor-core accumulation (KS = K-steps of 16 actions), or sampling only
-template <int NTHR, int NPASS, int MMA>
+template <int NTHR, int NT, int NPASS, int MMA>
 static int launch_demo16_mma(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
                              uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
-    using C = DemoCfg<16, 128, NPASS>;
-    const int smem = (MMA > 0 ? C::rec_region(R) + 4 * acc16::WARP_WORDS * 4 : 0) + C::TG * 4 + 16 + 2 * 128 * 4;
+    using C = DemoCfg<16, NT, NPASS>;
+    const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : 0) + C::TG * 4 + 16 + 2 * NT * 4;
     if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
-    auto kern = demo_kernel<16, 128, NPASS, true, NTHR, false, MMA>;
+    auto kern = demo_kernel<16, NT, NPASS, true, NTHR, false, MMA>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(int)grid, 128, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
+    kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
@@ -534,12 +534,13 @@ static int dispatch_demo16_mma(unsigned long long first, long long N, int R, int
                                uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
     if (variant == 9) { // two kernels: sample, then sum from the tape
-        const int rc = launch_demo16_mma<NTHR, 4, -1>(first, N, R, shift, cat, max_tries, tape, stride, nullptr, flags, st);
+        const int rc = launch_demo16_mma<NTHR, 128, 4, -1>(first, N, R, shift, cat, max_tries, tape, stride, nullptr, flags, st);
         return rc != TG_OK ? rc : launch_demo_acc16_mma(tape, stride, N, R, shift, slab, flags, 1, st);
     }
-    if (R <= 32) return launch_demo16_mma<NTHR, 2, 2>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    if (variant == 8) return launch_demo16_mma<NTHR, 1, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-    return launch_demo16_mma<NTHR, 2, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    if (R <= 32) return launch_demo16_mma<NTHR, 128, 2, 2>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    if (variant == 8) return launch_demo16_mma<NTHR, 128, 1, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+    // measured (profiles/README.md): 16-demo tiles 0.504 ms per 2^17 demos, 8-demo tiles 0.535, 256-thread CTAs 0.534
+    return launch_demo16_mma<NTHR, 128, 2, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
 }
 
 template <bool SAMPLE, int NTHR>
