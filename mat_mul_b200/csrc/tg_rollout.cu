@@ -11,9 +11,15 @@
 // step costs one pack(v w) and S IMADs per thread.  Only the tokens stream
 // from HBM (TP bytes per game-step) through a small shared-memory ring that a
 // dedicated producer warp keeps full with TMA bulk copies (full/empty
-// mbarriers).  "Is the game solved" is one shared-memory vote + one named
-// barrier of the compute warps per step.  HBM traffic per game: 2*GP + K*TP + 9
-// bytes.
+// mbarriers).  "Is the game solved" is decided lazily: a thread notes, per step,
+// whether ITS words are all zero (one bit), and only every SEG = 8 steps the bit
+// masks of a game's threads are AND-ed through shared memory (three named
+// barriers of the compute warps per 8 steps instead of one per step, so the
+// warps drift freely inside a segment).  A game solved at step t of a segment
+// keeps computing until the segment ends; that is harmless: frozen at the zero
+// tensor means its result IS the zero tensor, `steps` comes from the first set
+// bit, and range checks made after t are discarded.  HBM traffic per game:
+// 2*GP + K*TP + 9 bytes.
 #include "tg_step.cuh"
 
 namespace tg {
@@ -24,6 +30,7 @@ struct RollCfg {
     static constexpr int TG = NT / G::WR;      // games per CTA (one word column per thread)
     static constexpr int ACTIVE = TG * G::WR;
     static constexpr int TOK_BYTES = TG * G::TP;
+    static constexpr int SEG = 8;              // steps between two game-level "solved?" reductions
     static constexpr int SMEM_BYTES = NST * TOK_BYTES + 4 * TG * 4 + 2 * TG * 4 + 2 * NST * 8;
     static_assert((NST & (NST - 1)) == 0, "ring depth must be a power of two");
 };
@@ -52,7 +59,8 @@ __global__ void __launch_bounds__(NT + 32)
     Lane<S> L;
     L.init(tid < C::ACTIVE ? tid % G::WR : 0);
 
-    for (int i = tid; i < 4 * C::TG; i += NT + 32) s_any[i] = 0;
+    // s_any[0][g]: AND of the per-thread "my words are zero" step masks of game g; s_any[3][g]: initial state non-zero
+    for (int i = tid; i < 4 * C::TG; i += NT + 32) s_any[i] = i < C::TG ? 0xFFFFFFFFu : 0u;
     for (int i = tid; i < C::TG; i += NT + 32) s_sum[i] = 0, s_steps[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < NST; s++) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], NT / 32);
@@ -97,11 +105,10 @@ __global__ void __launch_bounds__(NT + 32)
         }
     } else {
         const uint8_t *tok0 = s_tok + g * G::TP;
+        uint32_t zmask = 0, bmask = 0; // per step of the current segment: my words all zero / my range check failed
         for (int t = 0; t < K; t++) {
             const int st = t & (NST - 1);
             mbar_wait(&s_full[st], (uint32_t)(t / NST) & 1u);
-            // slot (t+2)&3 was last read right after the barrier of step t-2: every warp is past the barrier of t-1
-            if (tid < C::TG) s_any[((t + 2) & 3) * C::TG + tid] = 0;
             if (alive) {
                 const uint8_t *tok = tok0 + st * C::TOK_BYTES;
                 const int32_t vw = pack_vw<S>(tok, L, shift);
@@ -116,16 +123,41 @@ __global__ void __launch_bounds__(NT + 32)
                 }
                 if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
                     until = chk;
+                    uint32_t b = 0;
 #pragma unroll
-                    for (int i = 0; i < S; i++) bad |= ~(row[i] ^ (row[i] << 1));
+                    for (int i = 0; i < S; i++) b |= ~(row[i] ^ (row[i] << 1));
+                    if (freeze)
+                        bmask |= ((b & L.hv) != 0 ? 1u : 0u) << (t & (C::SEG - 1));
+                    else
+                        bad |= b;
                 }
                 my_steps = t + 1;
-                if (any & vmask) s_any[(t & 3) * C::TG + g] = 1;
+                if ((any & vmask) == 0) zmask |= 1u << (t & (C::SEG - 1));
             }
             __syncwarp();
             if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
-            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); // compute warps only
-            if (alive && freeze) alive = s_any[(t & 3) * C::TG + g] != 0;
+            if (freeze && ((t & (C::SEG - 1)) == C::SEG - 1 || t == K - 1)) {
+                // ---- segment end: has the game been all zero at some step of the segment?
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); // the masks of the previous segment have been re-armed
+                if (alive) atomicAnd(&s_any[g], zmask);
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+                const uint32_t solved = alive ? (s_any[g] & (0xFFFFFFFFu >> (31 - (t & (C::SEG - 1))))) : 0u;
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+                if (tid < C::TG) s_any[tid] = 0xFFFFFFFFu;
+                if (alive) {
+                    if (solved) {
+                        const int first = __ffs(solved) - 1; // frozen from this step on: the zero tensor
+                        my_steps = (t & ~(C::SEG - 1)) + first + 1;
+                        alive = false;
+#pragma unroll
+                        for (int i = 0; i < S; i++) row[i] = H4;
+                        if (bmask & (0xFFFFFFFFu >> (31 - first))) bad = 0xFFFFFFFFu;
+                    } else if (bmask) {
+                        bad = 0xFFFFFFFFu;
+                    }
+                }
+                zmask = 0, bmask = 0;
+            }
         }
     }
 

@@ -32,7 +32,8 @@ S, R, K, shift = 9, 23, 64, 2
 lay = env.layout(S)
 print(f"rollout sweep {S}x{S}x{S}, K={K} (R={R} real actions + null padding), one B200")
 print(f"{'games':>10} {'fused ms':>10} {'fused Gsteps/s':>15} {'hbm_frac':>9} {'per-step ms':>12} {'per-step Gsteps/s':>18} {'solved':>8}")
-for lb in (14, 16, 18, 20, 22, 24):
+LBS = tuple(int(x) for x in sys.argv[1].split(",")) if len(sys.argv) > 1 else (14, 16, 18, 20, 22, 24)
+for lb in LBS:
     B = 1 << lb
     tape, slab, _ = env.make_synthetic_demos(B, R, S, V5, P5, shift, seed=lb)
     tapeK = torch.empty((K, B, lay.token_pitch), dtype=torch.uint8, device="cuda")
