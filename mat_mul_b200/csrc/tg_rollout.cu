@@ -106,9 +106,10 @@ __global__ void __launch_bounds__(NT + 32)
     } else {
         const uint8_t *tok0 = s_tok + g * G::TP;
         uint32_t zmask = 0, bmask = 0; // per step of the current segment: my words all zero / my range check failed
-        for (int t = 0; t < K; t++) {
-            const int st = t & (NST - 1);
-            mbar_wait(&s_full[st], (uint32_t)(t / NST) & 1u);
+        // one step; `st` is a literal in the unrolled main loop, so every shared-memory address of the step is
+        // (per-thread register + immediate)
+        auto step = [&](int t, int st, uint32_t parity) {
+            mbar_wait(&s_full[st], parity);
             if (alive) {
                 const uint8_t *tok = tok0 + st * C::TOK_BYTES;
                 const int32_t vw = pack_vw<S>(tok, L, shift);
@@ -136,29 +137,39 @@ __global__ void __launch_bounds__(NT + 32)
             }
             __syncwarp();
             if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[st])) : "memory");
-            if (freeze && ((t & (C::SEG - 1)) == C::SEG - 1 || t == K - 1)) {
-                // ---- segment end: has the game been all zero at some step of the segment?
-                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); // the masks of the previous segment have been re-armed
-                if (alive) atomicAnd(&s_any[g], zmask);
-                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-                const uint32_t solved = alive ? (s_any[g] & (0xFFFFFFFFu >> (31 - (t & (C::SEG - 1))))) : 0u;
-                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-                if (tid < C::TG) s_any[tid] = 0xFFFFFFFFu;
-                if (alive) {
-                    if (solved) {
-                        const int first = __ffs(solved) - 1; // frozen from this step on: the zero tensor
-                        my_steps = (t & ~(C::SEG - 1)) + first + 1;
-                        alive = false;
+        };
+        // segment end after step t: has the game been all zero at some step of the segment?
+        auto segment_end = [&](int t) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); // the masks of the previous segment have been re-armed
+            if (alive) atomicAnd(&s_any[g], zmask);
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+            const uint32_t solved = alive ? (s_any[g] & (0xFFFFFFFFu >> (31 - (t & (C::SEG - 1))))) : 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+            if (tid < C::TG) s_any[tid] = 0xFFFFFFFFu;
+            if (alive) {
+                if (solved) {
+                    const int first = __ffs(solved) - 1; // frozen from this step on: the zero tensor
+                    my_steps = (t & ~(C::SEG - 1)) + first + 1;
+                    alive = false;
 #pragma unroll
-                        for (int i = 0; i < S; i++) row[i] = H4;
-                        if (bmask & (0xFFFFFFFFu >> (31 - first))) bad = 0xFFFFFFFFu;
-                    } else if (bmask) {
-                        bad = 0xFFFFFFFFu;
-                    }
+                    for (int i = 0; i < S; i++) row[i] = H4;
+                    if (bmask & (0xFFFFFFFFu >> (31 - first))) bad = 0xFFFFFFFFu;
+                } else if (bmask) {
+                    bad = 0xFFFFFFFFu;
                 }
-                zmask = 0, bmask = 0;
             }
+            zmask = 0, bmask = 0;
+        };
+        static_assert(C::SEG % NST == 0, "a segment is a whole number of ring turns");
+        int t = 0;
+        for (; t + NST <= K; t += NST) {
+            const uint32_t parity = (uint32_t)(t / NST) & 1u;
+#pragma unroll
+            for (int q = 0; q < NST; q++) step(t + q, q, parity);
+            if (freeze && ((t + NST) & (C::SEG - 1)) == 0) segment_end(t + NST - 1);
         }
+        for (; t < K; t++) step(t, t & (NST - 1), (uint32_t)(t / NST) & 1u);
+        if (freeze && (K & (C::SEG - 1)) != 0) segment_end(K - 1);
     }
 
     // final state out, per-game nnz / flags / steps

@@ -70,10 +70,11 @@ __device__ __forceinline__ int32_t pack_vw(const uint8_t *tok, const Lane<S> &L,
         const int vB = (int)tok[L.off_vB] - shift;
         const uint32_t wt = (uint32_t)tok[L.off_w[0]] | ((uint32_t)tok[L.off_w[1]] << 8) |
                             ((uint32_t)tok[L.off_w[2]] << 16) | ((uint32_t)tok[L.off_w[3]] << 24);
-        const uint32_t sh = (uint32_t)shift * ONES4;
-        const int32_t wsA = (int32_t)((wt & L.maskA) - (sh & L.maskA));
+        // integer form of the valid bytes, ws = wsA + wsB, so vA wsA + vB wsB = vA ws + (vB - vA) wsB
+        const uint32_t sh = (uint32_t)shift * ONES4, mv = L.maskA | L.maskB;
+        const int32_t ws = (int32_t)((wt & mv) - (sh & mv));
         const int32_t wsB = (int32_t)((wt & L.maskB) - (sh & L.maskB));
-        return vA * wsA + vB * wsB;
+        return vA * ws + (vB - vA) * wsB;
     }
 }
 
