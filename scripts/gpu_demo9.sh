@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:demo_kernel -s 2 -c 1 -o gpurun_out/prof_demo_S9c -f python scripts/prof_demo.py 9 > gpurun_out/ncu_demo9c.log 2>&1
-tail -1 gpurun_out/ncu_demo9c.log
+timeout 900 python -m pytest tests/test_demo_gen_gpu.py tests/test_configs_gpu.py tests/test_dropin_gpu.py tests/test_step_gpu.py tests/test_rollout_ustream_gpu.py -x -q -m gpu 2>&1 | tail -4
+python scripts/time_kernels.py 2>&1 | grep -E "demo_gen|accumulate" | tee gpurun_out/time_demo_sparse.txt
