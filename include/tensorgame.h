@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TG_VERSION 101
+#define TG_VERSION 102
 
 #define TG_OK 0
 #define TG_E_ARG (-1)     /* bad argument (unsupported S, null pointer, misaligned buffer) */

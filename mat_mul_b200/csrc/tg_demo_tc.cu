@@ -1,6 +1,7 @@
 // tg_demo_tc.cu -- K3t: the target tensor of a 16x16x16 action list on the 5th-generation tensor cores
-// (tcgen05.mma kind::i8, accumulators in TMEM).  Used by tg_demo_accumulate / tg_demo_gen_philox for S = 16,
-// R <= 64, where the packed-IMAD accumulation of tg_demo.cu is issue-bound (784 FMA-pipe cycles per demo).
+// (tcgen05.mma kind::i8, accumulators in TMEM): the experimental entry point tg_demo_accumulate_tc (S = 16, R <= 64).
+// tg_demo_accumulate / tg_demo_gen_philox use the mma.sync f16 kernel of tg_demo_mma.cu instead, which is 1.5x faster
+// than this one (profiles/README.md).
 //
 // Reference restated: target = sum_r u_r (x) v_r (x) w_r (utils.py:40-53 uvw_to_demo, utils.py:232,
 // datasets.py:141).  As a GEMM per demo:
@@ -14,8 +15,8 @@
 //
 // STATUS: experimental.  Bit-exact against the packed-IMAD path for every R <= 64, but only 1.3x faster (0.23 ms vs
 // 0.30 ms for 65536 demos, R = 49): with MN-major no-swizzle int8 operands each tcgen05.mma costs ~350 cycles whatever its
-// size, so the four MMAs of a demo pace the CTA at ~1450 cycles per demo (profiles/README.md).  tg_demo_accumulate keeps the
-// packed-IMAD kernel; this entry point stays for tests, profiling and the next round.
+// size, so the four MMAs of a demo pace the CTA at ~1450 cycles per demo (profiles/README.md).  This entry point stays for
+// tests and profiling.
 //
 // Warp-specialised CTA, rings of mbarriers (no CTA-wide barrier in the loop):
 //   producers (8 warps): thread (r, quarter) turns action r of the demo (tape rows prefetched from HBM one demo
