@@ -209,7 +209,7 @@ def cpu_reference_leg(S: int, shift: int, seconds: float = 12.0):
 
     from oracle import tg_oracle as orc
 
-    cores = orc.num_threads()
+    cores = orc.use_all_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every core regardless
     Bs = 1 << 16
     rng = np.random.default_rng(0)
     T = (rng.integers(-2, 3, (Bs, S, S, S)) * (rng.random((Bs, S, S, S)) < 0.3)).astype(np.float32)

@@ -734,3 +734,14 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* all the host threads the process may use, whatever OMP_NUM_THREADS said at start-up (torchrun exports
+ * OMP_NUM_THREADS=1 to its workers); returns the new thread count */
+int orc_use_all_threads(void) {
+#ifdef _OPENMP
+    omp_set_num_threads(omp_get_num_procs());
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

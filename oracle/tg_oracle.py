@@ -275,3 +275,8 @@ def state_key_batch(T) -> np.ndarray:
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def use_all_threads() -> int:
+    """OpenMP threads = every core the process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    return int(lib().orc_use_all_threads())
