@@ -129,3 +129,22 @@ def test_full_size_16_tensor_core_paths_by_invariants(env):
     sq = lambda x: (x.to(torch.int32) ** 2).sum(dim=1)
     assert torch.equal(sq(t1), sq(slab))
     assert torch.equal(t1.to(torch.int16).abs().sort(dim=1).values[:: 257], slab.to(torch.int16).abs().sort(dim=1).values[:: 257])
+
+
+@pytest.mark.parametrize("S,R,N", [(9, 23, 1 << 18), (4, 7, 1 << 20)])
+def test_full_size_change_of_basis_round_trip(env, S, R, N):
+    """Change of basis at bench scale (no oracle at this size): signed permutation matrices per game, then their transposes,
+    give the original tensors back; the sum of squares of every game is unchanged; range flags follow the entries."""
+    vals, probs, shift = (V3, P3, 1) if S == 4 else (V5, P5, 2)
+    _, slab, flags = env.make_synthetic_demos(N, R, S, vals, probs, shift, seed=77)
+    g = torch.Generator(device="cuda").manual_seed(S)
+    perm = torch.rand((N, 3, S), device="cuda", generator=g).argsort(dim=-1)
+    sign = (torch.randint(0, 2, (N, 3, S), device="cuda", generator=g) * 2 - 1).to(torch.int8)
+    mats = torch.zeros((N, 3, S, S), dtype=torch.int8, device="cuda")
+    mats.scatter_(3, perm.unsqueeze(-1), sign.unsqueeze(-1))
+    t1, f1 = env.change_of_basis(slab, mats, S)
+    back, f2 = env.change_of_basis(t1, mats.transpose(2, 3).contiguous(), S)
+    assert torch.equal(back, slab)
+    assert torch.equal(f1 & 4, flags & 4) and torch.equal(f2 & 4, flags & 4) and not ((f1 | f2) & 0x80).any()
+    sq = lambda x: (x.to(torch.int32) ** 2).sum(dim=1)
+    assert torch.equal(sq(t1), sq(slab))
