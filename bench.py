@@ -277,10 +277,9 @@ def main() -> None:
     dev = torch.device("cuda", local)
     numa_cores = env.bind_host_to_gpu(local)  # pinned staging buffers of the e2e leg land on the GPU's NUMA node
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION, which this image
-        # exports) out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's own log (its version banner at NCCL_DEBUG=VERSION/WARN, which the GPU
+        # boxes export) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     S, shift, B, K, W = args.size, 2, args.games, args.steps, max(args.warmup, 3)
