@@ -279,7 +279,9 @@ def main() -> None:
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own log (its version banner at NCCL_DEBUG=VERSION/WARN, which the GPU
         # boxes export) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # honoured above the VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # the banner-only level always prints to stdout
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
 
     S, shift, B, K, W = args.size, 2, args.games, args.steps, max(args.warmup, 3)
