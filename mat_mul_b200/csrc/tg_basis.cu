@@ -233,8 +233,14 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
         const int8_t *m = mats + (g0 + gl) * mat_stride;
         // one matrix row per thread and step: A and B rows -> int32 (padded to RW, read as int4 later) and their
         // 1-norms, C rows -> bytes packed four to a word
-        for (int r = t; r < 3 * S; r += F::TPG) {
-            const int f = r / S, row = r % S;
+        // TPG == S (S = 4, 9): thread t takes row t of A, of B and of C -- f and row are compile-time after unrolling, and the
+        // 3 S byte loads of a thread are all in flight before the first is used
+        constexpr int RSTEPS = F::TPG == S ? 3 : (3 * S + F::TPG - 1) / F::TPG;
+#pragma unroll
+        for (int rs = 0; rs < RSTEPS; rs++) {
+            const int r = t + rs * F::TPG;
+            if (F::TPG != S && r >= 3 * S) break;
+            const int f = F::TPG == S ? rs : r / S, row = F::TPG == S ? t : r % S;
             int v[RW];
 #pragma unroll
             for (int a = 0; a < RW; a++) v[a] = a < S ? (int)m[f * S2 + row * S + a] : 0;

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:basis_fast -s 2 -c 1 -o gpurun_out/prof_basis_S9c -f python scripts/prof_basis.py 9 > gpurun_out/ncu_basis9c.log 2>&1
-tail -1 gpurun_out/ncu_basis9c.log
+timeout 900 python -m pytest tests/test_aux_basis_gpu.py tests/test_configs_gpu.py -x -q -m gpu 2>&1 | tail -3
+python scripts/time_kernels.py 2>&1 | grep -E "change_of_basis" | tee gpurun_out/time_basis_setup.txt
