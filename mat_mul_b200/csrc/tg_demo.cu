@@ -466,7 +466,16 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
         }
     }
     if constexpr (C::OVERLAY) __syncthreads(); // every record has been consumed: the slab tile takes over the same bytes
-    if (worker) {
+    if constexpr (S == 4) {
+        // 4x4x4: a game is 64 bytes and thread j holds one aligned word of each of its four rows: straight to HBM (the four
+        // threads of a game fill 16 contiguous bytes per store; a bulk store per 64-byte game costs ~10 warp-instructions)
+        if (worker) {
+            uint32_t *gdst = reinterpret_cast<uint32_t *>(slab + (g0 + g) * G::GP) + j;
+#pragma unroll
+            for (int i = 0; i < S; i++) gdst[i * (G::RP / 4)] = (uint32_t)acc[i][0];
+            if (bad) atomicOr(&s_flag[g], (uint32_t)TG_FLAG_RANGE);
+        }
+    } else if (worker) {
         // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k; the last j also zeroes the row padding,
         // j = 0 the game padding
         uint8_t *gbase = s_slab + (size_t)g * C::PITCH + j * S;
@@ -499,12 +508,16 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     fence_proxy_async();
     __syncthreads();
 
-    // ---------------- C. tile out: one bulk store per game
-    for (int gg = tid; gg < ng; gg += NT) bulk_s2g(slab + (g0 + gg) * G::GP, s_slab + (size_t)gg * C::PITCH, (uint32_t)G::GP);
-    if (tid < ng) bulk_commit();
+    // ---------------- C. tile out: one bulk store per game (S = 4 wrote its games from registers)
+    if constexpr (S != 4) {
+        for (int gg = tid; gg < ng; gg += NT) bulk_s2g(slab + (g0 + gg) * G::GP, s_slab + (size_t)gg * C::PITCH, (uint32_t)G::GP);
+        if (tid < ng) bulk_commit();
+    }
     if (flags)
         for (int gg = tid; gg < ng; gg += NT) flags[g0 + gg] = (uint8_t)s_flag[gg];
-    if (tid < ng) bulk_wait<0>();
+    if constexpr (S != 4) {
+        if (tid < ng) bulk_wait<0>();
+    }
 }
 
 template <int S, int NT, int NPASS, bool SAMPLE, int NTHR>
