@@ -481,14 +481,27 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
         uint8_t *gbase = s_slab + (size_t)g * C::PITCH + j * S;
 #pragma unroll
         for (int i = 0; i < S; i++) {
+            if constexpr (S == 9) {
+                // the 9-byte run starts at byte 9j of the row: parity j & 1.  Four aligned halfwords (bytes sj .. sj+7 of the
+                // run, funnel-shifted into place) and one single byte (the first for odd j, the last for even j) instead of
+                // nine byte stores
+                const int sj = j & 1;
+                const uint32_t w0 = (uint32_t)acc[i][0], w1 = (uint32_t)acc[i][1], w2 = (uint32_t)acc[i][2];
+                const uint32_t x0 = __funnelshift_r(w0, w1, 8 * sj), x1 = __funnelshift_r(w1, w2, 8 * sj);
+                uint8_t *rowp = gbase + i * G::RP;
+                uint16_t *hp = reinterpret_cast<uint16_t *>(rowp + sj);
+                hp[0] = (uint16_t)x0, hp[1] = (uint16_t)(x0 >> 16), hp[2] = (uint16_t)x1, hp[3] = (uint16_t)(x1 >> 16);
+                rowp[sj ? 0 : 8] = (uint8_t)(sj ? w0 : w2);
+            } else {
 #pragma unroll
-            for (int m = 0; m < KW; m++) {
-                const uint32_t t = (uint32_t)acc[i][m];
-                if constexpr (S % 4 == 0) {
-                    reinterpret_cast<uint32_t *>(gbase + i * G::RP)[m] = t;
-                } else {
+                for (int m = 0; m < KW; m++) {
+                    const uint32_t t = (uint32_t)acc[i][m];
+                    if constexpr (S % 4 == 0) {
+                        reinterpret_cast<uint32_t *>(gbase + i * G::RP)[m] = t;
+                    } else {
 #pragma unroll
-                    for (int k = 4 * m; k < S && k < 4 * m + 4; k++) gbase[i * G::RP + k] = (uint8_t)(t >> (8 * (k & 3)));
+                        for (int k = 4 * m; k < S && k < 4 * m + 4; k++) gbase[i * G::RP + k] = (uint8_t)(t >> (8 * (k & 3)));
+                    }
                 }
             }
             if constexpr (G::RP != G::S2) {
