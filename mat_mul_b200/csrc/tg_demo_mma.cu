@@ -102,6 +102,7 @@ bool demo_acc16_mma_applies(int R) { return R >= 1 && R <= 64; }
 int launch_demo_acc16_mma(const uint8_t *tape, long long tape_step_stride, long long N, int R, int shift, int8_t *slab,
                           uint8_t *flags, int or_flags, cudaStream_t st) {
     constexpr int SMEM = WARPS * WARP_WORDS * 4;
+    if ((N + WARPS - 1) / WARPS > 0x7FFFFFFFLL) return TG_E_ARG;
     const unsigned grid = (unsigned)((N + WARPS - 1) / WARPS);
     static const int variant = getenv("TG_ACC_VARIANT") ? atoi(getenv("TG_ACC_VARIANT")) : 0; // tuning sweeps only
     const int pf = (variant & 1) ? PREFETCH_CTAS : 0;
