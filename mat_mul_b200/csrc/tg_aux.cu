@@ -25,6 +25,35 @@ __device__ __forceinline__ void vw_bytes(const uint8_t *tok, const Lane<S> &L, i
     }
 }
 
+// four consecutive float32 entries of one output row (entries 4c .. 4c+3, the first nv of them inside the row) leave with
+// the widest stores the address allows: one 16-byte store when S^2 is a multiple of four (4x4x4, 16x16x16: every run of a
+// 16-byte aligned batch is aligned), at 9x9x9 (rows of 81 floats: the alignment of a run alternates with the row) two
+// 8-byte stores, or 4 + 8 + 4 bytes around the aligned pair in the middle
+template <int S>
+__device__ __forceinline__ void store_run(float *p, int nv, float a, float b, float c, float d) {
+    const uint32_t lo = (uint32_t)reinterpret_cast<uintptr_t>(p);
+    if constexpr (Geo<S>::S2 % 4 == 0) {
+        if ((lo & 15u) == 0) {
+            *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+            return;
+        }
+    }
+    if (nv == 4) {
+        if ((lo & 7u) == 0) {
+            *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+            *reinterpret_cast<float2 *>(p + 2) = make_float2(c, d);
+        } else {
+            p[0] = a;
+            *reinterpret_cast<float2 *>(p + 1) = make_float2(b, c);
+            p[3] = d;
+        }
+    } else {
+        if (nv > 0) p[0] = a;
+        if (nv > 1) p[1] = b;
+        if (nv > 2) p[2] = c;
+    }
+}
+
 // PACK16: the head is accumulated two entries per 32-bit word (16-bit lanes in integer form, one IMAD per two
 // entries, half the registers -> more samples in flight); the host takes this path when R * cmax^3 + 128 fits int16.
 // STAGE: the CTA first copies the action records a .. R-1 of all its samples into shared memory, every load in flight at
@@ -71,6 +100,7 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
     // head
     float *st = states + b * (long long)dim_t * G::S3;
     const int8_t *tg = slab + demo * G::GP + 4 * L.c;
+    const int nv = min(4, G::S2 - 4 * L.c); // entries of this word column inside a row (the last column of 9x9x9 holds one)
     if constexpr (PACK16) {
         int acc[S][2];
 #pragma unroll
@@ -92,14 +122,16 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
             }
         }
 #pragma unroll
-        for (int i = 0; i < S; i++)
+        for (int i = 0; i < S; i++) {
+            float f[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int x = acc[i][q >> 1];
                 const int lo = (int)(short)(x & 0xFFFF);
-                const int v = (q & 1) ? (x - lo) >> 16 : lo;
-                if (4 * L.c + q < G::S2) st[i * G::S2 + 4 * L.c + q] = (float)v;
+                f[q] = (float)((q & 1) ? (x - lo) >> 16 : lo);
             }
+            store_run<S>(st + i * G::S2 + 4 * L.c, nv, f[0], f[1], f[2], f[3]);
+        }
     } else {
         int acc[S][4];
 #pragma unroll
@@ -119,9 +151,7 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
         }
 #pragma unroll
         for (int i = 0; i < S; i++)
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (4 * L.c + q < G::S2) st[i * G::S2 + 4 * L.c + q] = (float)acc[i][q];
+            store_run<S>(st + i * G::S2 + 4 * L.c, nv, (float)acc[i][0], (float)acc[i][1], (float)acc[i][2], (float)acc[i][3]);
     }
     // history slots: rank-1 tensors of the next actions, latest first
     const int hi = min(a + dim_t, R);
@@ -135,16 +165,11 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
 #pragma unroll
             for (int i = 0; i < S; i++) {
                 const int u = (int)tok[i] - replay_shift;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (4 * L.c + q < G::S2) ss[i * G::S2 + 4 * L.c + q] = (float)(u * vw[q]);
+                store_run<S>(ss + i * G::S2 + 4 * L.c, nv, (float)(u * vw[0]), (float)(u * vw[1]), (float)(u * vw[2]), (float)(u * vw[3]));
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < S; i++)
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (4 * L.c + q < G::S2) ss[i * G::S2 + 4 * L.c + q] = 0.f;
+            for (int i = 0; i < S; i++) store_run<S>(ss + i * G::S2 + 4 * L.c, nv, 0.f, 0.f, 0.f, 0.f);
         }
     }
     if (L.c == 0) {
