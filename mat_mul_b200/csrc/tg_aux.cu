@@ -1,4 +1,6 @@
 // tg_aux.cu -- K4 demo_sample (training-sample batcher), K6 slice_rank, K7 state_key.
+#include <type_traits>
+
 #include "tg_step.cuh"
 
 namespace tg {
@@ -14,14 +16,35 @@ namespace tg {
 // there, callers wanting the true residual pass the demo's shift.
 // One thread per (sample, word column); per-entry int32 accumulators, so any
 // magnitude the float32 reference can hold exactly is exact here too.
-template <int S>
-__device__ __forceinline__ void vw_bytes(const uint8_t *tok, const Lane<S> &L, int shift, int vw[4]) {
+template <int S, typename TB>
+__device__ __forceinline__ void vw_bytes(const TB *tok, const Lane<S> &L, int shift, int vw[4]) {
     const int vA = (int)tok[L.off_vA] - shift, vB = (int)tok[L.off_vB] - shift;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
         const bool inA = (L.maskA >> (8 * b)) & 1u, inB = (L.maskB >> (8 * b)) & 1u;
         const int w = (int)tok[L.off_w[b]] - shift;
         vw[b] = inA ? vA * w : (inB ? vB * w : 0);
+    }
+}
+
+// sign-extended byte B of a word (one PRMT with a sign-replicating selector)
+template <int B>
+__device__ __forceinline__ int sext_byte(uint32_t w) {
+    constexpr uint32_t sel = (uint32_t)B | ((uint32_t)(B | 8) << 4) | ((uint32_t)(B | 8) << 8) | ((uint32_t)(B | 8) << 12);
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "r"(sel));
+    return (int)d;
+}
+
+// sample index -> (demo, action); indices below 2^32 (every realistic store) take a 32-bit division
+__device__ __forceinline__ void split_index(long long id, int R, long long &demo, int &a) {
+    if ((unsigned long long)id < 0x100000000ULL) {
+        const uint32_t d = (uint32_t)id / (uint32_t)R;
+        demo = (long long)d;
+        a = (int)((uint32_t)id - d * (uint32_t)R);
+    } else {
+        demo = id / R;
+        a = (int)(id - demo * R);
     }
 }
 
@@ -67,58 +90,113 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
                                    float *__restrict__ scalars, long long *__restrict__ actions,
                                    float *__restrict__ rewards) {
     using G = Geo<S>;
+    // COEF (the production variant): the staged records after the sample's own action hold int8 coefficients; exact under the
+    // same contract PACK16 already needs (tokens <= 8, 0 <= replay_shift <= 8)
+    constexpr bool COEF = PACK16 && STAGE;
     extern __shared__ __align__(16) uint8_t s_tok[]; // STAGE: [samples of the CTA][R][TP]
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long b = t / G::WR;
     const long long b0 = (blockIdx.x * (long long)blockDim.x) / G::WR; // first sample this CTA touches
+    // this thread's own sample first: its index and the words of the target it owns are in flight while the CTA stages the
+    // action records (otherwise a third dependent DRAM round trip after the barrier)
+    Lane<S> L;
+    L.init((int)(t % G::WR));
+    long long demo = -1;
+    int a = 0;
+    if (b < nb) split_index(idx[b], R, demo, a);
+    const bool live = b < nb && demo >= 0 && demo < N;
+    uint32_t head[S];
+    if (live) {
+        const int8_t *tg = slab + demo * G::GP + 4 * L.c;
+#pragma unroll
+        for (int i = 0; i < S; i++) head[i] = __ldg(reinterpret_cast<const uint32_t *>(tg + i * G::RP));
+    }
     if constexpr (STAGE) {
         constexpr int SLOTS = (128 + G::WR - 1) / G::WR + 1;
         const int nslots = (int)min((long long)SLOTS, nb - b0);
         for (int item = threadIdx.x; item < nslots * R; item += 128) {
             const int sl = item / R, j = item - sl * R;
-            const long long id2 = idx[b0 + sl];
-            const long long demo2 = id2 / R;
-            const int a2 = (int)(id2 - demo2 * R);
+            long long demo2;
+            int a2;
+            split_index(idx[b0 + sl], R, demo2, a2);
             if (demo2 >= 0 && demo2 < N && j >= a2) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(tape + (size_t)j * tape_step_stride + demo2 * G::TP);
                 uint4 *dst = reinterpret_cast<uint4 *>(s_tok + ((size_t)sl * R + j) * G::TP);
+                if (COEF && j > a2) {
+                    // records that are only ever replayed are staged as int8 coefficients (token - replay_shift, no borrow
+                    // between bytes: token | 0x80 > shift), so the replay loop needs no subtraction per byte
+                    const uint32_t sh4 = (uint32_t)replay_shift * ONES4;
 #pragma unroll
-                for (int w = 0; w < G::TP / 16; w++) dst[w] = __ldg(src + w);
+                    for (int w = 0; w < G::TP / 16; w++) {
+                        const uint4 x = __ldg(src + w);
+                        dst[w] = make_uint4(((x.x | H4) - sh4) ^ H4, ((x.y | H4) - sh4) ^ H4, ((x.z | H4) - sh4) ^ H4, ((x.w | H4) - sh4) ^ H4);
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < G::TP / 16; w++) dst[w] = __ldg(src + w);
+                }
             }
         }
         __syncthreads();
     }
-    if (b >= nb) return;
-    Lane<S> L;
-    L.init((int)(t % G::WR));
-    const long long id = idx[b];
-    const long long demo = id / R;
-    const int a = (int)(id - demo * R);
-    if (demo < 0 || demo >= N) return;
+    if (!live) return;
     const uint8_t *tk = STAGE ? s_tok + (size_t)(b - b0) * R * G::TP : tape + demo * G::TP;
     if constexpr (STAGE) tape_step_stride = G::TP;
     // head
     float *st = states + b * (long long)dim_t * G::S3;
-    const int8_t *tg = slab + demo * G::GP + 4 * L.c;
     const int nv = min(4, G::S2 - 4 * L.c); // entries of this word column inside a row (the last column of 9x9x9 holds one)
     if constexpr (PACK16) {
         int acc[S][2];
 #pragma unroll
         for (int i = 0; i < S; i++) {
-            const uint32_t t = *reinterpret_cast<const uint32_t *>(tg + i * G::RP);
+            const uint32_t t = head[i];
             acc[i][0] = (int)(int8_t)(t & 0xFFu) + ((int)(int8_t)((t >> 8) & 0xFFu)) * 65536;
             acc[i][1] = (int)(int8_t)((t >> 16) & 0xFFu) + ((int)(int8_t)(t >> 24)) * 65536;
         }
-        for (int j = a + 1; j < R; j++) {
-            const uint8_t *tok = tk + (size_t)j * tape_step_stride;
-            int vw[4];
-            vw_bytes<S>(tok, L, replay_shift, vw);
-            const int p0 = vw[0] + vw[1] * 65536, p1 = vw[2] + vw[3] * 65536;
+        if constexpr (COEF) {
+            // entries outside the row (last word column of 9x9x9) pick up a v of their own; they are never stored and a low
+            // 16-bit lane does not depend on the lane above it
+            const bool inA0 = !G::STRADDLE || (L.maskA & 0x1u), inA1 = !G::STRADDLE || (L.maskA & 0x100u),
+                       inA2 = !G::STRADDLE || (L.maskA & 0x10000u), inA3 = !G::STRADDLE || (L.maskA & 0x1000000u);
+            const int8_t *rec = reinterpret_cast<const int8_t *>(tk) + (size_t)(a + 1) * G::TP;
+#pragma unroll 2
+            for (int j = a + 1; j < R; j++, rec += G::TP) {
+                const int nvA = -(int)rec[L.off_vA], nvB = G::STRADDLE ? -(int)rec[L.off_vB] : nvA;
+                const int w0 = rec[L.off_w[0]], w1 = rec[L.off_w[1]], w2 = rec[L.off_w[2]], w3 = rec[L.off_w[3]];
+                const int np0 = (inA0 ? nvA : nvB) * w0 + ((inA1 ? nvA : nvB) * w1) * 65536;
+                const int np1 = (inA2 ? nvA : nvB) * w2 + ((inA3 ? nvA : nvB) * w3) * 65536;
+                uint32_t uq[4];
+                if constexpr (S <= 4) {
+                    uq[0] = *reinterpret_cast<const uint32_t *>(rec);
+                } else {
+                    const uint4 q4 = *reinterpret_cast<const uint4 *>(rec);
+                    uq[0] = q4.x, uq[1] = q4.y, uq[2] = q4.z, uq[3] = q4.w;
+                }
 #pragma unroll
-            for (int i = 0; i < S; i++) {
-                const int u = (int)tok[i] - replay_shift;
-                acc[i][0] -= u * p0;
-                acc[i][1] -= u * p1;
+                for (int i = 0; i < S; i++) {
+                    int u;
+                    switch (i & 3) {
+                    case 0: u = sext_byte<0>(uq[i >> 2]); break;
+                    case 1: u = sext_byte<1>(uq[i >> 2]); break;
+                    case 2: u = sext_byte<2>(uq[i >> 2]); break;
+                    default: u = sext_byte<3>(uq[i >> 2]); break;
+                    }
+                    acc[i][0] += u * np0;
+                    acc[i][1] += u * np1;
+                }
+            }
+        } else {
+            for (int j = a + 1; j < R; j++) {
+                const uint8_t *tok = tk + (size_t)j * tape_step_stride;
+                int vw[4];
+                vw_bytes<S, uint8_t>(tok, L, replay_shift, vw);
+                const int p0 = vw[0] + vw[1] * 65536, p1 = vw[2] + vw[3] * 65536;
+#pragma unroll
+                for (int i = 0; i < S; i++) {
+                    const int u = (int)tok[i] - replay_shift;
+                    acc[i][0] -= u * p0;
+                    acc[i][1] -= u * p1;
+                }
             }
         }
 #pragma unroll
@@ -137,11 +215,11 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
 #pragma unroll
         for (int i = 0; i < S; i++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) acc[i][q] = (int)tg[i * G::RP + q];
+            for (int q = 0; q < 4; q++) acc[i][q] = (int)(int8_t)((head[i] >> (8 * q)) & 0xFFu);
         for (int j = a + 1; j < R; j++) {
             const uint8_t *tok = tk + (size_t)j * tape_step_stride;
             int vw[4];
-            vw_bytes<S>(tok, L, replay_shift, vw);
+            vw_bytes<S, uint8_t>(tok, L, replay_shift, vw);
 #pragma unroll
             for (int i = 0; i < S; i++) {
                 const int u = (int)tok[i] - replay_shift;
@@ -159,12 +237,14 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
         const int j = hi - s;
         float *ss = st + (long long)s * G::S3;
         if (j >= a + 1) {
-            const uint8_t *tok = tk + (size_t)j * tape_step_stride;
+            using TB = typename std::conditional<COEF, int8_t, uint8_t>::type; // COEF: the record already holds coefficients
+            const int hshift = COEF ? 0 : replay_shift;
+            const TB *tok = reinterpret_cast<const TB *>(tk + (size_t)j * tape_step_stride);
             int vw[4];
-            vw_bytes<S>(tok, L, replay_shift, vw);
+            vw_bytes<S, TB>(tok, L, hshift, vw);
 #pragma unroll
             for (int i = 0; i < S; i++) {
-                const int u = (int)tok[i] - replay_shift;
+                const int u = (int)tok[i] - hshift;
                 store_run<S>(ss + i * G::S2 + 4 * L.c, nv, (float)(u * vw[0]), (float)(u * vw[1]), (float)(u * vw[2]), (float)(u * vw[3]));
             }
         } else {
