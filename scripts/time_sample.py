@@ -9,7 +9,10 @@ from mat_mul_b200 import env
 
 torch.manual_seed(0)
 V5, P5 = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05)
+ONLY = int(os.environ.get('TS_ONLY', '0'))
 for S, R, N, vals, probs, shift in [(4, 7, 1 << 20, (-1, 0, 1), (0.15, 0.7, 0.15), 1), (9, 23, 1 << 18, V5, P5, 2), (16, 49, 1 << 15, V5, P5, 2)]:
+    if ONLY and S != ONLY:
+        continue
     tape, slab, _ = env.make_synthetic_demos(N, R, S, vals, probs, shift, seed=1)
     for T in (2, 4):
         idx = torch.randint(0, N * R, (1 << 16,), device="cuda")
