@@ -58,6 +58,35 @@ def test_demo_sample_random_vs_oracle(env, S, R, dim_t):
     assert np.array_equal(st[:, 0].cpu().numpy(), first.astype(np.float32))
 
 
+@pytest.mark.parametrize("S,R,dim_t", [(4, 7, 1), (9, 23, 3), (9, 23, 2), (16, 12, 3)])
+def test_demo_sample_every_store_alignment(env, S, R, dim_t):
+    # the output rows leave as 16-byte / 8-byte / 4+8+4-byte stores depending on the address of each run of four floats:
+    # every sample of the batch against the oracle, with the states buffer starting at each 4-byte offset of a 16-byte
+    # line (called through the C ABI with a caller-owned, offset buffer)
+    from mat_mul_b200 import _lib
+    from mat_mul_b200.env import _p, _stream, check, layout
+
+    N, shift = 12, 2
+    tok, tgt, _ = orc.demos_seeded(9, V5, P5, R, S, shift, N)
+    tape = torch.from_numpy(tokens_to_tape3(tok)).cuda()
+    slab = torch.from_numpy(dense_to_slab(tgt)).cuda()
+    idx_np = np.random.default_rng(1).permutation(N * R)[:97]
+    idx = torch.from_numpy(idx_np).cuda()
+    nb, per = len(idx_np), dim_t * S**3
+    want = np.stack([orc.demo_getitem(tok[i // R], tgt[i // R], dim_t, i % R, replay_shift=shift)[0] for i in idx_np]).astype(np.float32)
+    for off in range(4):
+        buf = torch.full((nb * per + 8,), -77.0, dtype=torch.float32, device="cuda")
+        states = buf[off:off + nb * per]
+        scalars = torch.empty((nb, 1), dtype=torch.float32, device="cuda")
+        actions = torch.empty((nb, 3 * S), dtype=torch.int64, device="cuda")
+        rewards = torch.empty((nb, 1), dtype=torch.float32, device="cuda")
+        check(_lib.lib().tg_demo_sample(_p(tape), N * layout(S).token_pitch, _p(slab), N, R, S, dim_t, shift, _p(idx), nb,
+                                        _p(states), _p(scalars), _p(actions), _p(rewards), _stream()), "tg_demo_sample")
+        got = buf.cpu().numpy()
+        assert np.array_equal(got[off:off + nb * per].reshape(want.shape), want), off
+        assert (got[:off] == -77.0).all() and (got[off + nb * per:] == -77.0).all(), off  # nothing outside the batch
+
+
 @pytest.mark.parametrize("S", [4, 9, 16])
 def test_slice_rank_matches_reference_get_rank(env, golden, S):
     g = golden["ranks"]
