@@ -68,7 +68,9 @@ int tg_layout(int S, int *row_pitch, int *game_pitch, int *token_pitch);
  * of utils.py:99-111 / datasets.py:94-114 at the boundary. */
 int tg_pack_f32(const float *src, int64_t src_stride, int8_t *slab, int64_t B, int S, int32_t *range_flag, void *stream);
 /* slab -> float32 dense (S,S,S) at dst + b*dst_stride: the state the model
- * consumes (model.py:101-103). */
+ * consumes (model.py:101-103).  The slab is 16-byte aligned like every slab;
+ * dst may start at any float (rows leave with the widest stores each address
+ * allows). */
 int tg_expand_f32(const int8_t *slab, float *dst, int64_t dst_stride, int64_t B, int S, void *stream);
 /* int64 tokens (B,3S) (reference action format, utils.py:56-66) <-> tape */
 int tg_pack_actions_i64(const int64_t *actions, uint8_t *tape, int64_t B, int S, int32_t *range_flag, void *stream);

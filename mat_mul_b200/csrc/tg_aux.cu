@@ -48,35 +48,6 @@ __device__ __forceinline__ void split_index(long long id, int R, long long &demo
     }
 }
 
-// four consecutive float32 entries of one output row (entries 4c .. 4c+3, the first nv of them inside the row) leave with
-// the widest stores the address allows: one 16-byte store when S^2 is a multiple of four (4x4x4, 16x16x16: every run of a
-// 16-byte aligned batch is aligned), at 9x9x9 (rows of 81 floats: the alignment of a run alternates with the row) two
-// 8-byte stores, or 4 + 8 + 4 bytes around the aligned pair in the middle
-template <int S>
-__device__ __forceinline__ void store_run(float *p, int nv, float a, float b, float c, float d) {
-    const uint32_t lo = (uint32_t)reinterpret_cast<uintptr_t>(p);
-    if constexpr (Geo<S>::S2 % 4 == 0) {
-        if ((lo & 15u) == 0) {
-            *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
-            return;
-        }
-    }
-    if (nv == 4) {
-        if ((lo & 7u) == 0) {
-            *reinterpret_cast<float2 *>(p) = make_float2(a, b);
-            *reinterpret_cast<float2 *>(p + 2) = make_float2(c, d);
-        } else {
-            p[0] = a;
-            *reinterpret_cast<float2 *>(p + 1) = make_float2(b, c);
-            p[3] = d;
-        }
-    } else {
-        if (nv > 0) p[0] = a;
-        if (nv > 1) p[1] = b;
-        if (nv > 2) p[2] = c;
-    }
-}
-
 // PACK16: the head is accumulated two entries per 32-bit word (16-bit lanes in integer form, one IMAD per two
 // entries, half the registers -> more samples in flight); the host takes this path when R * cmax^3 + 128 fits int16.
 // STAGE: the CTA first copies the action records a .. R-1 of all its samples into shared memory, every load in flight at

@@ -105,4 +105,84 @@ __device__ __forceinline__ uint32_t nonzero_mask(uint32_t x) { return (((x & 0x7
 // sum of the four unsigned bytes of x
 __device__ __forceinline__ uint32_t byte_sum(uint32_t x) { return __dp4a(x, ONES4, 0u); }
 
+// vector accesses as PTX, so that the access width is exactly the one the alignment test in front of it allows (the
+// compiler re-vectorised the plain C++ stores of the misaligned branch into an 8-byte store at p + 2)
+__device__ __forceinline__ void st_f32x4(float *p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_f32x2(float *p, float a, float b) {
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(__cvta_generic_to_global(p)), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_f32(float *p, float a) {
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(a) : "memory");
+}
+__device__ __forceinline__ void ld_f32x4(const float *p, float f[4]) {
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "l"(__cvta_generic_to_global(p)));
+}
+__device__ __forceinline__ void ld_f32x2(const float *p, float &a, float &b) {
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(__cvta_generic_to_global(p)));
+}
+__device__ __forceinline__ float ld_f32(const float *p) {
+    float a;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(a) : "l"(__cvta_generic_to_global(p)));
+    return a;
+}
+
+// four consecutive float32 entries of one output row (entries 4c .. 4c+3, the first nv of them inside the row) leave with
+// the widest stores the address allows: one 16-byte store when S^2 is a multiple of four (4x4x4, 16x16x16: every run of a
+// 16-byte aligned batch is aligned), at 9x9x9 (rows of 81 floats: the alignment of a run alternates with the row) two
+// 8-byte stores, or 4 + 8 + 4 bytes around the aligned pair in the middle.  p points to global memory.
+template <int S>
+__device__ __forceinline__ void store_run(float *p, int nv, float a, float b, float c, float d) {
+    const uint32_t lo = (uint32_t)reinterpret_cast<uintptr_t>(p);
+    if constexpr (Geo<S>::S2 % 4 == 0) {
+        if ((lo & 15u) == 0) {
+            st_f32x4(p, a, b, c, d);
+            return;
+        }
+    }
+    if (nv == 4) {
+        if ((lo & 7u) == 0) {
+            st_f32x2(p, a, b);
+            st_f32x2(p + 2, c, d);
+        } else {
+            st_f32(p, a);
+            st_f32x2(p + 1, b, c);
+            st_f32(p + 3, d);
+        }
+    } else {
+        if (nv > 0) st_f32(p, a);
+        if (nv > 1) st_f32(p + 1, b);
+        if (nv > 2) st_f32(p + 2, c);
+    }
+}
+
+// counterpart of store_run: four consecutive float32 entries of a row (the first nv of them exist) with the widest loads
+// the address allows
+template <int S>
+__device__ __forceinline__ void load_run(const float *p, int nv, float f[4]) {
+    const uint32_t lo = (uint32_t)reinterpret_cast<uintptr_t>(p);
+    f[0] = f[1] = f[2] = f[3] = 0.f;
+    if constexpr (Geo<S>::S2 % 4 == 0) {
+        if ((lo & 15u) == 0) {
+            ld_f32x4(p, f);
+            return;
+        }
+    }
+    if (nv == 4) {
+        if ((lo & 7u) == 0) {
+            ld_f32x2(p, f[0], f[1]);
+            ld_f32x2(p + 2, f[2], f[3]);
+        } else {
+            f[0] = ld_f32(p);
+            ld_f32x2(p + 1, f[1], f[2]);
+            f[3] = ld_f32(p + 3);
+        }
+    } else {
+        if (nv > 0) f[0] = ld_f32(p);
+        if (nv > 1) f[1] = ld_f32(p + 1);
+        if (nv > 2) f[2] = ld_f32(p + 2);
+    }
+}
+
 } // namespace tg

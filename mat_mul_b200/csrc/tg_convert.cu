@@ -6,7 +6,7 @@
 
 namespace tg {
 
-// one thread per 32-bit slab word; reads up to four floats
+// one thread per 32-bit slab word: four floats in with the widest loads their address allows (load_run)
 template <int S>
 __global__ void pack_f32_kernel(const float *__restrict__ src, long long src_stride, uint32_t *__restrict__ slab,
                                 long long B, int32_t *range_flag) {
@@ -21,16 +21,14 @@ __global__ void pack_f32_kernel(const float *__restrict__ src, long long src_str
         const int i = wg / G::WR, c = wg % G::WR;
         uint32_t word = 0;
         if (i < S) {
-            const float *row = src + b * src_stride + i * G::S2;
+            const int nv = min(4, G::S2 - 4 * c);
+            float f[4];
+            load_run<S>(src + b * src_stride + i * G::S2 + 4 * c, nv, f);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int jk = 4 * c + q;
-                if (jk < G::S2) {
-                    const float f = row[jk];
-                    const int v = __float2int_rn(f);
-                    bad |= ((float)v != f) | (v < -128) | (v > 127);
-                    word |= ((uint32_t)v & 0xFFu) << (8 * q);
-                }
+                const int v = __float2int_rn(f[q]); // entries beyond nv are 0.f
+                bad |= ((float)v != f[q]) | (v < -128) | (v > 127);
+                word |= ((uint32_t)v & 0xFFu) << (8 * q);
             }
         }
         slab[idx] = word;
@@ -38,18 +36,21 @@ __global__ void pack_f32_kernel(const float *__restrict__ src, long long src_str
     if (bad && range_flag) atomicOr(range_flag, 1);
 }
 
-// one thread per float entry
+// one thread per 32-bit slab word: four floats out with the widest stores their address allows (store_run)
 template <int S>
 __global__ void expand_f32_kernel(const int8_t *__restrict__ slab, float *__restrict__ dst, long long dst_stride,
                                   long long B) {
     using G = Geo<S>;
-    const long long total = B * G::S3;
+    constexpr int WG = S * G::WR; // words of the S rows (the game padding is not read)
+    const long long total = B * WG;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const long long b = idx / G::S3;
-        const int e = (int)(idx % G::S3);
-        const int i = e / G::S2, jk = e % G::S2;
-        dst[b * dst_stride + e] = (float)slab[b * G::GP + i * G::RP + jk];
+        const long long b = idx / WG;
+        const int wg = (int)(idx % WG);
+        const int i = wg / G::WR, c = wg % G::WR;
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(slab + b * G::GP + i * G::RP) + c);
+        store_run<S>(dst + b * dst_stride + i * G::S2 + 4 * c, min(4, G::S2 - 4 * c), (float)(int8_t)(w & 0xFFu),
+                     (float)(int8_t)((w >> 8) & 0xFFu), (float)(int8_t)((w >> 16) & 0xFFu), (float)(int8_t)(w >> 24));
     }
 }
 
@@ -107,7 +108,7 @@ extern "C" {
 int tg_pack_f32(const float *src, int64_t src_stride, int8_t *slab, int64_t B, int S, int32_t *range_flag, void *stream) {
     if (!tg::supported_S(S) || B < 0) return TG_E_ARG;
     if (B == 0) return TG_OK;
-    if (!src || !slab || ((uintptr_t)slab & 15)) return TG_E_ARG;
+    if (!src || !slab || ((uintptr_t)slab & 15) || ((uintptr_t)src & 3)) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     TG_DISPATCH_S(S, (tg::pack_f32_kernel<kS><<<tg::grid_for(B * (tg::Geo<kS>::GP / 4), 256), 256, 0, st>>>(
                          src, src_stride, reinterpret_cast<uint32_t *>(slab), B, range_flag)));
@@ -118,9 +119,9 @@ int tg_pack_f32(const float *src, int64_t src_stride, int8_t *slab, int64_t B, i
 int tg_expand_f32(const int8_t *slab, float *dst, int64_t dst_stride, int64_t B, int S, void *stream) {
     if (!tg::supported_S(S) || B < 0) return TG_E_ARG;
     if (B == 0) return TG_OK;
-    if (!slab || !dst) return TG_E_ARG;
+    if (!slab || !dst || ((uintptr_t)slab & 15) || ((uintptr_t)dst & 3)) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    TG_DISPATCH_S(S, (tg::expand_f32_kernel<kS><<<tg::grid_for(B * tg::Geo<kS>::S3, 256), 256, 0, st>>>(slab, dst, dst_stride, B)));
+    TG_DISPATCH_S(S, (tg::expand_f32_kernel<kS><<<tg::grid_for(B * kS * tg::Geo<kS>::WR, 256), 256, 0, st>>>(slab, dst, dst_stride, B)));
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }

@@ -126,6 +126,27 @@ def test_boundary_conversions(env, S):
         env.pack_states(state[:, 0] + 0.5, S)
 
 
+@pytest.mark.parametrize("S", [4, 9, 16])
+def test_boundary_conversions_every_alignment(env, S):
+    # the float32 side is read / written with 16-, 8- or 4-byte accesses chosen per run of four floats: games at every
+    # 4-byte alignment (odd batch stride, offset base pointer), nothing outside the games touched
+    rng = np.random.default_rng(6)
+    B, S3 = 257, S**3
+    dev = torch.device("cuda:0")
+    T = rng.integers(-128, 128, (B, S, S, S))
+    for off in range(4):
+        for stride in (S3 + 1, S3 + 2):
+            buf = torch.full((off + B * stride + 8,), -77.0, dtype=torch.float32, device=dev)
+            games = buf[off:off + B * stride].view(B, stride)[:, :S3].view(B, S, S, S)
+            games.copy_(torch.from_numpy(T).float().to(dev))
+            slab = env.pack_states(games, S)
+            assert np.array_equal(slab.cpu().numpy(), dense_to_slab(T)), (off, stride)
+            out = torch.full_like(buf, -77.0)
+            oview = out[off:off + B * stride].view(B, stride)[:, :S3].view(B, S, S, S)
+            env.expand_states(slab, S, out=oview)
+            assert torch.equal(out, buf), (off, stride)  # games identical, the gaps and both ends untouched
+
+
 @pytest.mark.parametrize("S", [4, 9])
 def test_host_path_matches_device_path(env, S):
     rng = np.random.default_rng(6)
