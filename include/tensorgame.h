@@ -28,6 +28,14 @@
  *                          for the next step to be guaranteed (TG_FLAG_RANGE).
  *   tape   uint8 [B][TP]   action tokens cat(u,v,w)+shift in bytes [0,3S),
  *                          TP = roundup16(3S) (16/32/48), padding zero.
+ *                          Token bound: every token is <= 2*shift (|coefficient|
+ *                          <= shift <= 4) for the shift handed to the same call;
+ *                          tg_step, tg_rollout, tg_replay and tg_expand_children
+ *                          test it and raise TG_FLAG_RANGE for a game whose
+ *                          record breaks it (its result is then unspecified).
+ *                          A caller with another token convention re-bases:
+ *                          coefficient c = token - s is passed as token c + 4
+ *                          with shift 4.
  *   flags  uint8 [B]       TG_FLAG_* bits per game.
  *   nnz    int32 [B]       count of non-zero residual entries (rank upper
  *                          bound, training.py:259-266).
@@ -41,7 +49,7 @@
 extern "C" {
 #endif
 
-#define TG_VERSION 102
+#define TG_VERSION 200
 
 #define TG_OK 0
 #define TG_E_ARG (-1)     /* bad argument (unsupported S, null pointer, misaligned buffer) */
@@ -50,7 +58,7 @@ extern "C" {
 
 #define TG_FLAG_TERMINAL 1u /* new head all zero: utils.py:181-188 on the head (act.py:177) */
 #define TG_FLAG_NULL 2u     /* rank-1 update all zero: utils.py:191-194 */
-#define TG_FLAG_RANGE 4u    /* a residual entry left [-64, 63]: int8 slab no longer guaranteed */
+#define TG_FLAG_RANGE 4u    /* a residual entry left [-64, 63] (int8 slab no longer guaranteed) or a token exceeded 2*shift */
 #define TG_FLAG_EXHAUSTED 8u /* demo generation: a term hit max_tries and was forced to a unit triple */
 #define TG_FLAG_TOKEN_RANGE 16u /* change of basis: a transformed factor entry left [-shift_out, shift_out] */
 
@@ -210,6 +218,23 @@ int tg_host_ctx_destroy(tg_host_ctx *ctx);
  * pipelined H2D -> kernel -> D2H over three streams; returns when done. */
 int tg_step_host(tg_host_ctx *ctx, const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags,
                  int32_t *nnz, int64_t B, int shift);
+/* tg_rollout with HOST buffers: the slab crosses PCIe once per K steps instead of once per step -- the case where the
+ * caller holds the whole action list (SyntheticDemoDataset._take_actions, datasets.py:144-153).  tape is the dense
+ * step-major host tape uint8 [K][B][TP]. */
+int tg_rollout_host(tg_host_ctx *ctx, const int8_t *slab_in, const uint8_t *tape, int K, int8_t *slab_out, uint8_t *flags,
+                    int32_t *nnz, int32_t *steps, int64_t B, int shift);
+/* tg_demo_gen_philox into HOST buffers (dense step-major tape uint8 [R][N][TP], slab [N][GP], flags [N]): chunks are
+ * generated on the device and copied out over three streams; the end-to-end form of utils.py:203-233 /
+ * datasets.py:124-142 for a caller that wants the demonstrations in host memory. */
+int tg_demo_gen_host(tg_host_ctx *ctx, uint64_t seed, uint64_t first_demo, int64_t N, int R, int shift, const int8_t *values,
+                     const double *probs, int n_values, int max_tries, uint8_t *tape, int8_t *slab, uint8_t *flags);
+
+#ifdef TG_TUNING
+/* Sweep build only (-DTG_TUNING, libtensorgame_b200_tuning.so): CTAs launched per SM (0 = default) and kernel
+ * variant of tg_step; the production library does not export them. */
+int tg_tune_step_ctas_per_sm(int n);
+int tg_tune_step_variant(int v);
+#endif
 
 #ifdef __cplusplus
 }

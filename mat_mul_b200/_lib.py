@@ -12,7 +12,11 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-LIB_PATH = PKG / "libtensorgame_b200.so"
+# TG_TUNING=1 selects the sweep build (-DTG_TUNING: extra kernel instantiations, getenv knobs, tg_tune_* entry points);
+# the production library has none of them
+TUNING = os.environ.get("TG_TUNING", "0") not in ("", "0")
+LIB_PATH = PKG / ("libtensorgame_b200_tuning.so" if TUNING else "libtensorgame_b200.so")
+HASH_PATH = LIB_PATH.with_suffix(".srchash")
 HEADER = PKG.parent / "include" / "tensorgame.h"
 
 NVCC_FLAGS = [
@@ -36,12 +40,28 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (sources, header, flags): unlike mtimes it survives the
+    copy to the GPU box, so a shipped .so is recognised as current there and a stale one is recognised as stale."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + (["-DTG_TUNING"] if TUNING else [])).encode())
+    for d in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh"))) + [HEADER]:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HEADER]
-    return any(d.stat().st_mtime > t for d in deps)
+    return HASH_PATH.read_text().strip() != _source_hash()
+
+
+def header_version() -> int:
+    import re
+
+    return int(re.search(r"#define\s+TG_VERSION\s+(\d+)", HEADER.read_text()).group(1))
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -49,12 +69,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, sources())]
+    cmd = [nvcc, *NVCC_FLAGS, *(["-DTG_TUNING"] if TUNING else []), "-o", str(LIB_PATH), *map(str, sources())]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    digest = _source_hash()
+    HASH_PATH.unlink(missing_ok=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise TensorGameError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    HASH_PATH.write_text(digest + "\n")
     if verbose:
         print(res.stderr)
     return LIB_PATH
@@ -98,9 +121,13 @@ _SIGNATURES = {
     "tg_host_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int64]),
     "tg_host_ctx_destroy": (C.c_int, [_vp]),
     "tg_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
-    "tg_tune_step_ctas_per_sm": (C.c_int, [C.c_int]),
-    "tg_tune_step_variant": (C.c_int, [C.c_int]),
+    "tg_rollout_host": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
+    "tg_demo_gen_host": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                   _vp, _vp, _vp]),
 }
+if TUNING:  # sweep build only (declared under TG_TUNING in include/tensorgame.h)
+    _SIGNATURES["tg_tune_step_ctas_per_sm"] = (C.c_int, [C.c_int])
+    _SIGNATURES["tg_tune_step_variant"] = (C.c_int, [C.c_int])
 
 
 def exported_symbols() -> list[str]:
@@ -108,6 +135,8 @@ def exported_symbols() -> list[str]:
     import re
 
     text = HEADER.read_text()
+    if not TUNING:  # the sweep-only entry points exist in the -DTG_TUNING build alone
+        text = re.sub(r"#ifdef TG_TUNING.*?#endif", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -115,18 +144,21 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if _stale():
+            # never load a library built from other sources: the ctypes signatures below describe THIS tree
             try:
                 build()
             except (TensorGameError, FileNotFoundError) as e:
-                if not LIB_PATH.exists():
-                    raise TensorGameError(
-                        "libtensorgame_b200.so is missing and could not be built; "
-                        "run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)"
-                    ) from e
+                raise TensorGameError(
+                    f"{LIB_PATH.name} is missing or older than its sources and could not be rebuilt; "
+                    "run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)"
+                ) from e
         handle = C.CDLL(str(LIB_PATH))
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        if handle.tg_version() != header_version():
+            raise TensorGameError(f"{LIB_PATH.name} reports tg_version {handle.tg_version()}, include/tensorgame.h "
+                                  f"declares {header_version()}: rebuild the library")
         _lib = handle
     return _lib
 

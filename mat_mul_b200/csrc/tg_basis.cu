@@ -30,8 +30,6 @@
 // int8 matrices); a thread owns one column of the contracted axis in registers
 // and produces its S outputs.  TG_FLAG_RANGE marks games whose T' leaves the
 // int8 slab's guaranteed zone [-64,63].
-#include <cstdlib>
-
 #include "tg_common.cuh"
 
 namespace tg {
@@ -689,7 +687,11 @@ int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, 
     } break;
     // S = 16: the tensor-core kernel (tg_basis_mma.cu) takes the place of the packed fast kernel; TG_BASIS_VARIANT=1
     // keeps the packed kernel (A/B timing only)
-    static const int variant = getenv("TG_BASIS_VARIANT") ? atoi(getenv("TG_BASIS_VARIANT")) : 0;
+#ifdef TG_TUNING
+    static const int variant = tg::tuning_env("TG_BASIS_VARIANT", 0);
+#else
+    constexpr int variant = 0;
+#endif
     if (S == 16 && flags && variant != 1 && (((uintptr_t)mats | (uintptr_t)ms) & 3) == 0) {
         const int rc = tg::launch_basis_mma16(slab_in, mats, ms, slab_out, flags, N, st);
         if (rc != TG_OK) return rc;

@@ -34,8 +34,6 @@
 // cvt.rn.f16x2.f32 issues beside it (profiles/README.md).
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "tg_common.cuh"
 
 namespace tg {
@@ -322,7 +320,6 @@ __global__ void __launch_bounds__(32 * WARPS, MINB)
 int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, int8_t *slab_out, uint8_t *flags,
                        long long N, cudaStream_t st) {
     constexpr int SMEM = WARPS * WARP_WORDS * 4;
-    static const int variant = getenv("TG_BASIS_VARIANT") ? atoi(getenv("TG_BASIS_VARIANT")) : 0; // tuning sweeps only
     const unsigned grid = (unsigned)((N + WARPS - 1) / WARPS);
 #define TG_MMA16_LAUNCH(MINB, STREAM, PATHS, PF)                                                                        \
     {                                                                                                                  \
@@ -330,11 +327,14 @@ int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                        \
         kern<<<grid, 32 * WARPS, SMEM, st>>>(slab_in, mats, mat_stride, slab_out, flags, N);                           \
     }
-    switch (variant) {
-    case 2: TG_MMA16_LAUNCH(4, true, 1, 0) break;  // 16-bit planes only
-    case 3: TG_MMA16_LAUNCH(4, false, 0, 0) break; // no L2 prefetch
-    default: TG_MMA16_LAUNCH(4, false, 0, 4) break; // measured best (profiles/README.md): prefetch one wave of CTAs ahead
+#ifdef TG_TUNING
+    switch (tuning_env("TG_BASIS_VARIANT", 0)) {
+    case 2: TG_MMA16_LAUNCH(4, true, 1, 0) return TG_OK;  // 16-bit planes only
+    case 3: TG_MMA16_LAUNCH(4, false, 0, 0) return TG_OK; // no L2 prefetch
+    default: break;
     }
+#endif
+    TG_MMA16_LAUNCH(4, false, 0, 4) // measured best (profiles/README.md): prefetch one wave of CTAs ahead
 #undef TG_MMA16_LAUNCH
     TG_CUDA(cudaGetLastError());
     return TG_OK;

@@ -26,6 +26,19 @@ __host__ __device__ constexpr bool supported_S(int S) { return S == 4 || S == 9 
 
 extern int g_last_cuda_error;
 
+// Kernel variants for tuning sweeps exist only in the -DTG_TUNING build (libtensorgame_b200_tuning.so, selected with
+// TG_TUNING=1 by mat_mul_b200/_lib.py): there an environment variable picks the variant; the production library compiles
+// the measured-best path alone and reads no environment.
+#ifdef TG_TUNING
+}
+#include <cstdlib>
+namespace tg {
+inline int tuning_env(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#endif
+
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return TG_E_CUDA;

@@ -29,8 +29,6 @@
 //      R * shift^3 a per-thread bound shift^2 * sum_r |v_rj| guards the packed
 //      path and the (rare) thread above it recomputes its entries one by one.
 //   C. the slab tile leaves through one TMA bulk store.
-#include <cstdlib>
-
 #include "tg_demo_mma.cuh"
 #include "tg_step.cuh"
 
@@ -576,13 +574,15 @@ static int launch_demo16_mma(unsigned long long first, long long N, int R, int s
 template <int NTHR>
 static int dispatch_demo16_mma(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
                                uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
-    static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+#ifdef TG_TUNING
+    static const int variant = tuning_env("TG_DEMO_VARIANT", 0);
     if (variant == 9) { // two kernels: sample, then sum from the tape
         const int rc = launch_demo16_mma<NTHR, 128, 4, -1>(first, N, R, shift, cat, max_tries, tape, stride, nullptr, flags, st);
         return rc != TG_OK ? rc : launch_demo_acc16_mma(tape, stride, N, R, shift, slab, flags, 1, st);
     }
-    if (R <= 32) return launch_demo16_mma<NTHR, 128, 2, 2>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
     if (variant == 8) return launch_demo16_mma<NTHR, 128, 1, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+#endif
+    if (R <= 32) return launch_demo16_mma<NTHR, 128, 2, 2>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
     // measured (profiles/README.md): 16-demo tiles 0.504 ms per 2^17 demos, 8-demo tiles 0.535, 256-thread CTAs 0.534
     return launch_demo16_mma<NTHR, 128, 2, 4>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
 }
@@ -592,36 +592,41 @@ static int dispatch_demo(unsigned long long first, long long N, int R, int S, in
                          int max_tries, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     switch (S) {
     case 4: { // big tiles (several passes of phase B) amortise the retry tail of the sampler; long action lists fall back
-        static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+#ifdef TG_TUNING
+        static const int variant = tuning_env("TG_DEMO_VARIANT", 0);
         if (variant == 1 && DemoCfg<4, 128, 8>::smem_bytes(R) <= 160 * 1024)
             return launch_demo<4, 128, 8, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         if (variant == 2 && DemoCfg<4, 128, 4>::smem_bytes(R) <= 160 * 1024)
             return launch_demo<4, 128, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         if (variant == 3 && DemoCfg<4, 512, 2>::smem_bytes(R) <= 160 * 1024)
             return launch_demo<4, 512, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+#endif
         if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
             return launch_demo<4, 256, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         return launch_demo<4, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
     }
     case 9: {
-        static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
-        switch (variant) {
+#ifdef TG_TUNING
+        switch (tuning_env("TG_DEMO_VARIANT", 0)) {
         case 1: return launch_demo<9, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-        case 2: return launch_demo<9, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         case 3: return launch_demo<9, 128, 3, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         case 4: return launch_demo<9, 192, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         case 5: return launch_demo<9, 64, 4, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-        default: // measured best (profiles/README.md): 128-thread CTAs; 28-demo tiles when sampling, 14-demo tiles (slab tile
-                 // overlaid on the records) when only accumulating
-            if (SAMPLE) return launch_demo<9, 128, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
-            return launch_demo<9, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        default: break;
         }
+#endif
+        // measured best (profiles/README.md): 128-thread CTAs; 28-demo tiles when sampling, 14-demo tiles (slab tile
+        // overlaid on the records) when only accumulating
+        if (SAMPLE) return launch_demo<9, 128, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+        return launch_demo<9, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
     }
     case 16: {
-        static const int variant = getenv("TG_DEMO_VARIANT") ? atoi(getenv("TG_DEMO_VARIANT")) : 0; // tuning sweeps only
+#ifdef TG_TUNING
+        static const int variant = tuning_env("TG_DEMO_VARIANT", 0);
         if (variant == 1) return launch_demo<16, 256, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         if (variant == 2) return launch_demo<16, 64, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
         if (variant == 3) return launch_demo<16, 128, 2, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st);
+#endif
         return launch_demo<16, 128, 1, SAMPLE, NTHR>(first, N, R, shift, cat, max_tries, tape, stride, slab, flags, st); // measured best
     }
     }
@@ -680,7 +685,11 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
     cudaStream_t st = (cudaStream_t)stream;
     // 16x16x16, R <= 64: the targets are summed on the tensor cores (tg_demo_mma.cuh) inside the sampling kernel;
     // TG_DEMO_MMA=0 keeps the packed-IMAD accumulation (A/B timing only)
-    static const int use_mma = getenv("TG_DEMO_MMA") ? atoi(getenv("TG_DEMO_MMA")) : 1;
+#ifdef TG_TUNING
+    static const int use_mma = tg::tuning_env("TG_DEMO_MMA", 1);
+#else
+    constexpr int use_mma = 1;
+#endif
     if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R)) {
         if (n_values <= 3) return tg::dispatch_demo16_mma<2>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
         if (n_values <= 5) return tg::dispatch_demo16_mma<4>(first_demo, N, R, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
@@ -700,7 +709,11 @@ int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N,
     if (!tape || !slab) return TG_E_ARG;
     if (((uintptr_t)tape | (uintptr_t)slab | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
     // 16x16x16: tensor cores (tg_demo_mma.cu); TG_DEMO_MMA=0 keeps the packed-IMAD kernel (A/B timing only)
-    static const int use_mma = getenv("TG_DEMO_MMA") ? atoi(getenv("TG_DEMO_MMA")) : 1;
+#ifdef TG_TUNING
+    static const int use_mma = tg::tuning_env("TG_DEMO_MMA", 1);
+#else
+    constexpr int use_mma = 1;
+#endif
     if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R))
         return tg::launch_demo_acc16_mma(tape, tape_step_stride, N, R, shift, slab, flags, 0, (cudaStream_t)stream);
     tg::Categorical cat = {};

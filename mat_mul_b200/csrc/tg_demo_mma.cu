@@ -18,7 +18,6 @@
 // A demo with a token outside [0, 2 shift] (not an action of this alphabet; its coefficient is int8(token - shift) in
 // the packed-IMAD kernel) is summed entry by entry in int32 instead -- identical results.
 // Measured against the packed-IMAD kernel of tg_demo.cu and the tcgen05 kernel of tg_demo_tc.cu: profiles/README.md.
-#include <cstdlib>
 
 #include "tg_demo_mma.cuh"
 
@@ -104,7 +103,8 @@ int launch_demo_acc16_mma(const uint8_t *tape, long long tape_step_stride, long 
     constexpr int SMEM = WARPS * WARP_WORDS * 4;
     if ((N + WARPS - 1) / WARPS > 0x7FFFFFFFLL) return TG_E_ARG;
     const unsigned grid = (unsigned)((N + WARPS - 1) / WARPS);
-    static const int variant = getenv("TG_ACC_VARIANT") ? atoi(getenv("TG_ACC_VARIANT")) : 0; // tuning sweeps only
+#ifdef TG_TUNING
+    static const int variant = tuning_env("TG_ACC_VARIANT", 0);
     const int pf = (variant & 1) ? PREFETCH_CTAS : 0;
 #define TG_ACC16_LAUNCH(KS)                                                                                            \
     if (variant & 2) {                                                                                                 \
@@ -116,6 +116,15 @@ int launch_demo_acc16_mma(const uint8_t *tape, long long tape_step_stride, long 
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                        \
         kern<<<grid, 32 * WARPS, SMEM, st>>>(tape, tape_step_stride, N, R, shift, slab, flags, or_flags, pf);          \
     }
+#else
+    const int pf = 0; // measured best (profiles/r01_time_demo16_mma.txt): four CTAs per SM, no L2 prefetch
+#define TG_ACC16_LAUNCH(KS)                                                                                            \
+    {                                                                                                                  \
+        auto kern = demo_acc16_mma_kernel<KS, 4>;                                                                      \
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                        \
+        kern<<<grid, 32 * WARPS, SMEM, st>>>(tape, tape_step_stride, N, R, shift, slab, flags, or_flags, pf);          \
+    }
+#endif
     switch ((R + 15) / 16) {
     case 1: TG_ACC16_LAUNCH(1) break;
     case 2: TG_ACC16_LAUNCH(2) break;

@@ -24,7 +24,6 @@
 //   MMA warp: per demo 2 x K/32 tcgen05.mma (128 x 16 x 32, int8 -> int32 in TMEM, 32 columns per demo);
 //   consumers (8 warps): tcgen05.ld 16 columns of their 32 lanes, saturate to int8, range-test, one 16-byte store
 //      per lane: a warp writes 512 contiguous bytes of the slab.
-#include <cstdlib>
 
 #include "tg_common.cuh"
 
@@ -325,7 +324,9 @@ int launch_demo_tc(const uint8_t *tape, long long stride, long long N, int R, in
     auto kern = tc::demo_tc_kernel;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     int per_sm = tc::CTAS_PER_SM; // limited by threads and shared memory
-    if (const char *e = getenv("TG_TC_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+#ifdef TG_TUNING
+    if (tuning_env("TG_TC_CTAS", 0) > 0) per_sm = tuning_env("TG_TC_CTAS", 0);
+#endif
     const long long grid = N < 148 * per_sm ? N : 148 * per_sm;
     // the kernel only ever SETS flag bytes
     if (flags) TG_CUDA(cudaMemsetAsync(flags, 0, (size_t)N, st));

@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(NT)
                     if (negu != 0 && vw != 0) h += (unsigned long long)(long long)negu * word_key(i, vwb);
                 }
             }
-            atomicAdd(&s_part[st * C::TG + g], make_partial(byte_sum(cnt), vw != 0 && uany != 0, (rng & L.hv) != 0));
+            atomicAdd(&s_part[st * C::TG + g], make_partial(byte_sum(cnt), vw != 0 && uany != 0,
+                                                            (rng & L.hv) != 0 || tokens_out_of_range<S>(tok, L, shift)));
             if constexpr (KEYS)
                 if (h) atomicAdd(&s_key[st * C::TG + g], h);
         }

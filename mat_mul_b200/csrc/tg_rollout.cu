@@ -132,6 +132,12 @@ __global__ void __launch_bounds__(NT + 32)
                     else
                         bad |= b;
                 }
+                if (tokens_out_of_range<S>(tok, L, shift)) { // tape contract (tg_step.cuh): the packed update may have aliased
+                    if (freeze)
+                        bmask |= 1u << (t & (C::SEG - 1));
+                    else
+                        bad = 0xFFFFFFFFu;
+                }
                 my_steps = t + 1;
                 if ((any & vmask) == 0) zmask |= 1u << (t & (C::SEG - 1));
             }

@@ -143,8 +143,10 @@ static int sm_count() {
     return cached[dev];
 }
 
+#ifdef TG_TUNING
 static int g_step_ctas_per_sm = 0; // 0 = per-size default
 static int g_step_variant = 0;     // tuning sweeps only
+#endif
 
 template <int S, int NT, int NPASS, int NSTAGE>
 static int launch_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz,
@@ -153,7 +155,9 @@ static int launch_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_
     auto kern = step_kernel<S, NT, NPASS, NSTAGE>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const long long ntiles = (B + C::TG - 1) / C::TG;
+#ifdef TG_TUNING
     if (g_step_ctas_per_sm > 0) ctas_per_sm = g_step_ctas_per_sm;
+#endif
     const long long cap = (long long)sm_count() * ctas_per_sm;
     const int grid = (int)(ntiles < cap ? ntiles : cap);
     kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(slab_in, tape, slab_out, flags, nnz, B, shift);
@@ -187,6 +191,7 @@ int tg_layout(int S, int *row_pitch, int *game_pitch, int *token_pitch) {
     return TG_OK;
 }
 
+#ifdef TG_TUNING
 // tuning knobs for bench sweeps: CTAs launched per SM (0 = default) and kernel variant
 int tg_tune_step_ctas_per_sm(int n) {
     tg::g_step_ctas_per_sm = n;
@@ -196,6 +201,7 @@ int tg_tune_step_variant(int v) {
     tg::g_step_variant = v;
     return TG_OK;
 }
+#endif
 
 int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags, int32_t *nnz, int64_t B, int S,
             int shift, void *stream) {
@@ -204,32 +210,29 @@ int tg_step(const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_
     if (!slab_in || !tape || !slab_out || !flags || !nnz) return TG_E_ARG;
     if (((uintptr_t)slab_in | (uintptr_t)slab_out | (uintptr_t)tape) & 15) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+#ifdef TG_TUNING
+    switch (S * 10 + tg::g_step_variant) { // sweep-only instantiations
+    case 41: return tg::launch_step<4, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 42: return tg::launch_step<4, 256, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 43: return tg::launch_step<4, 256, 8, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 91: return tg::launch_step<9, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
+    case 92: return tg::launch_step<9, 256, 1, 4>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
+    case 93: return tg::launch_step<9, 256, 4, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 94: return tg::launch_step<9, 512, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 3, st);
+    case 95: return tg::launch_step<9, 128, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 7, st);
+    case 96: return tg::launch_step<9, 128, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
+    case 97: return tg::launch_step<9, 256, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 161: return tg::launch_step<16, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 162: return tg::launch_step<16, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 163: return tg::launch_step<16, 512, 1, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    default: break;
+    }
+#endif
+    // measured best (profiles/r01_sweep_step_S9.txt): 32 short CTAs per SM, two-stage ring
     switch (S) {
-    case 4:
-        switch (tg::g_step_variant) {
-        case 1: return tg::launch_step<4, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        case 2: return tg::launch_step<4, 256, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        case 3: return tg::launch_step<4, 256, 8, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        default: return tg::launch_step<4, 256, 4, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        }
-    case 9:
-        switch (tg::g_step_variant) {
-        case 1: return tg::launch_step<9, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
-        case 2: return tg::launch_step<9, 256, 1, 4>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
-        case 3: return tg::launch_step<9, 256, 4, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        case 4: return tg::launch_step<9, 512, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 3, st);
-        case 5: return tg::launch_step<9, 128, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 7, st);
-        case 6: return tg::launch_step<9, 128, 4, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 5, st);
-        case 7: return tg::launch_step<9, 256, 2, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        default: return tg::launch_step<9, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        }
-    case 16:
-        switch (tg::g_step_variant) {
-        case 1: return tg::launch_step<16, 256, 1, 3>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        case 2: return tg::launch_step<16, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        case 3: return tg::launch_step<16, 512, 1, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        default: return tg::launch_step<16, 256, 1, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
-        }
+    case 4: return tg::launch_step<4, 256, 4, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 9: return tg::launch_step<9, 256, 2, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
+    case 16: return tg::launch_step<16, 256, 1, 2>(slab_in, tape, slab_out, flags, nnz, B, shift, 32, st);
     }
     return TG_E_ARG;
 }

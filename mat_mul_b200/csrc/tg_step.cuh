@@ -14,8 +14,9 @@
 //        T' <- T' - u_i * VW ,   VW = sum_b v[j_b] w[k_b] 256^b
 // i.e. ONE 32-bit IMAD per four entries, exact as long as every resulting
 // entry stays in [-128,127].  That is guaranteed while residuals are in
-// [-64,63] and |u v w| <= 64 (shift <= 4); leaving that zone raises
-// TG_FLAG_RANGE for the game (the step that raised it is still exact).
+// [-64,63] and |u v w| <= 64 (shift <= 4, tokens <= 2 * shift); leaving that
+// zone -- or a token above 2 * shift -- raises TG_FLAG_RANGE for the game (a
+// step that left the zone with legal tokens is still exact).
 #pragma once
 #include "tg_common.cuh"
 
@@ -30,10 +31,12 @@ struct Lane {
     uint32_t maskB;   // bytes that belong to j = jA + 1 (STRADDLE only)
     int off_vA, off_vB; // token byte offsets of v[jA], v[jA+1]
     int off_w[4];       // token byte offsets of w[k_b]; [0] is word aligned when !STRADDLE
+    int tokw;           // the 32-bit word of the game's token record this thread range-checks (tokens_out_of_range)
 
     __device__ __forceinline__ void init(int c_) {
         using G = Geo<S>;
         c = c_;
+        tokw = c_ % (G::TP / 4);
         const int jk0 = 4 * c;
         const int jA = jk0 / S;
         hv = 0, maskA = 0, maskB = 0;
@@ -78,6 +81,16 @@ __device__ __forceinline__ int32_t pack_vw(const uint8_t *tok, const Lane<S> &L,
     }
 }
 
+// Tape contract: every token byte is <= 2 * shift, i.e. |coefficient| <= shift -- the bound the packed arithmetic relies
+// on (|u v w| <= shift^3 <= 64 per step).  Thread c tests word c % (TP / 4) of its game's record; the WR >= TP / 4
+// threads of a game cover the whole record.  A violation raises TG_FLAG_RANGE for the game.
+template <int S>
+__device__ __forceinline__ bool tokens_out_of_range(const uint8_t *tok, const Lane<S> &L, int shift) {
+    static_assert(Geo<S>::WR >= Geo<S>::TP / 4, "not enough threads per game to cover the token record");
+    const uint32_t x = reinterpret_cast<const uint32_t *>(tok)[L.tokw];
+    return ((((x & 0x7F7F7F7Fu) + (uint32_t)(0x7F - 2 * shift) * ONES4) | x) & H4) != 0;
+}
+
 // coefficient u_i = token_i - shift from the packed u tokens: one dp4a against a one-hot byte vector
 __device__ __forceinline__ int coef_u(const uint32_t uw[4], int i, int shift) {
     return (int)__dp4a(uw[i >> 2], 1u << (8 * (i & 3)), (uint32_t)(-shift));
@@ -117,7 +130,7 @@ __device__ __forceinline__ uint32_t rank1_update(uint8_t *game, const uint8_t *t
         rng |= t ^ (t << 1);
         uany |= negu;
     }
-    return make_partial(byte_sum(cnt), vw != 0 && uany != 0, (rng & L.hv) != 0);
+    return make_partial(byte_sum(cnt), vw != 0 && uany != 0, (rng & L.hv) != 0 || tokens_out_of_range<S>(tok, L, shift));
 }
 
 // nnz / range of a game without changing it (used for the initial state of a rollout)

@@ -101,6 +101,9 @@ class SyntheticDemoDataset(Dataset):
         """Collated batch for many indices at once (one tg_demo_sample launch): states (B,T,S,S,S) f32,
         scalars (B,1) f32, actions (B,3S) i64, rewards (B,1) f32 on self.device."""
         idx = torch.as_tensor(indices, dtype=torch.int64).to(self._cuda)
+        n_items = self._slab.shape[0] * self.max_actions
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_items):
+            raise IndexError(f"sample index out of range [0, {n_items})")
         # the reference replays with action_to_tensor, whose shift is fixed at 1 (SURVEY Q1)
         out = _env.demo_samples(self._tape, self._slab, idx, self.dim_3d, self.dim_t, replay_shift=1)
         return tuple(t.to(self.device) for t in out)
@@ -137,9 +140,11 @@ class SyntheticDemoDataset(Dataset):
         S = target_tensor.shape[-1]
         dev = _device()
         tokens = torch.stack([a.reshape(-1) for a in action_seq]).to(dev).to(torch.int64)
-        tape = _env.pack_actions(tokens, S).unsqueeze(1)
+        # coefficient = token - 1 (action_to_tensor's fixed shift), re-based to (token + 3, shift 4) so that
+        # the kernels' token bound holds for every alphabet the reference's datasets use
+        tape = _env.pack_actions(tokens, S, rebase=_COEF_SHIFT - 1).unsqueeze(1)
         slab = _env.pack_states(target_tensor.reshape(1, S, S, S).to(dev).float().contiguous(), S)
-        out, flags, _ = _env.replay(slab, tape, S, 1)
+        out, flags, _ = _env.replay(slab, tape, S, _COEF_SHIFT)
         if bool((flags & _env.FLAG_RANGE).any()):
             raise TensorGameError("_take_actions left the int8 slab's guaranteed range [-64, 63]")
         return _env.expand_states(out, S)[0].to(target_tensor.device)
@@ -186,7 +191,8 @@ class PlayedGamesDataset(Dataset):
 
     def add_game(self, state_seq: List[torch.Tensor], action_seq: List[torch.Tensor], reward_seq: List[torch.Tensor]):
         self.game_lengths[self.game_pointer] = len(state_seq)
-        self._games[self.game_pointer] = (state_seq, action_seq, reward_seq)
+        # snapshot (the reference wrote the sequences to disk): later mutation by the caller must not change the buffer
+        self._games[self.game_pointer] = (list(state_seq), list(action_seq), list(reward_seq))
         self.game_pointer = (self.game_pointer + 1) % self.buffer_size
 
 

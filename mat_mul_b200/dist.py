@@ -31,22 +31,49 @@ def shard_sizes(n_total: int, world_size: int) -> list[int]:
     return [shard_range(n_total, r, world_size)[1] - shard_range(n_total, r, world_size)[0] for r in range(world_size)]
 
 
-def gather_shards(shard: torch.Tensor, n_total: int, dim: int = 0) -> torch.Tensor:
+def gather_shards(shard: torch.Tensor, n_total: int, dim: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
     """All-gather per-rank shards (split along `dim` by shard_range) into the full tensor on every rank.
-    Fixed-size records: shards are padded to the largest shard so one all_gather_into_tensor suffices."""
+
+    Equal shard sizes (n_total divisible by the world size -- the bench and the datasets arrange that): ONE
+    all_gather_into_tensor per leading index, straight into the caller's (or a freshly allocated) full tensor --
+    no staging copy, no torch.cat.  `shard` may already be the rank's slice of `out` (NCCL's in-place all-gather).
+    dim > 0 (a step-major tape (R, N, TP) sharded over N) issues one collective per leading index, all in flight
+    at once.  Unequal shards take the padded path (one collective, then the pad rows are dropped)."""
     rank, ws = world()
     if ws == 1:
+        if out is not None and out.data_ptr() != shard.data_ptr():
+            out.copy_(shard)
+            return out
         return shard
     sizes = shard_sizes(n_total, ws)
     assert shard.shape[dim] == sizes[rank], (shard.shape, sizes, rank)
+    full_shape = list(shard.shape)
+    full_shape[dim] = n_total
+    lead1 = all(shard.shape[d] == 1 for d in range(dim))  # the shards are contiguous pieces of the full tensor
+    if len(set(sizes)) == 1 and (lead1 or dim == 1):
+        if out is None:
+            out = shard.new_empty(full_shape)
+        assert list(out.shape) == full_shape and out.is_contiguous()
+        if lead1:
+            dist.all_gather_into_tensor(out.view(-1), shard.contiguous().view(-1))
+        else:  # dim == 1: row r of the full tensor is the concatenation of row r of every shard
+            works = [dist.all_gather_into_tensor(out[r].view(-1), shard[r].contiguous().view(-1), async_op=True)
+                     for r in range(shard.shape[0])]
+            for w in works:
+                w.wait()
+        return out
     x = shard.movedim(dim, 0).contiguous()
     pad = max(sizes) - x.shape[0]
     if pad:
         x = torch.cat((x, x.new_zeros((pad, *x.shape[1:]))))
-    out = x.new_empty((ws * max(sizes), *x.shape[1:]))
-    dist.all_gather_into_tensor(out, x)
-    parts = [out[r * max(sizes) : r * max(sizes) + sizes[r]] for r in range(ws)]
-    return torch.cat(parts).movedim(0, dim).contiguous()
+    buf = x.new_empty((ws * max(sizes), *x.shape[1:]))
+    dist.all_gather_into_tensor(buf, x)
+    parts = [buf[r * max(sizes) : r * max(sizes) + sizes[r]] for r in range(ws)]
+    res = torch.cat(parts).movedim(0, dim).contiguous()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 @dataclass
@@ -96,4 +123,29 @@ def make_synthetic_demos_sharded(n_total: int, max_actions: int, S: int, values,
         tape = gather_shards(tape, n_total, dim=1)
         slab = gather_shards(slab, n_total, dim=0)
         flags = gather_shards(flags, n_total, dim=0)
+    return tape, slab, flags
+
+
+def make_synthetic_demos_gathered(n_total: int, max_actions: int, S: int, values, probs, shift: int, seed: int = 0, device=None):
+    """Every rank ends up with ALL n_total demos: each generates its contiguous slice [lo, hi) straight into its
+    rows of the full slab / columns of the full step-major tape, then the slices are all-gathered in place (the
+    shard handed to NCCL is a view of the output).  Requires n_total divisible by the world size."""
+    from . import env
+
+    rank, ws = world()
+    if n_total % ws:
+        raise ValueError("make_synthetic_demos_gathered needs n_total divisible by the world size")
+    lo, hi = shard_range(n_total, rank, ws)
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    lay = env.layout(S)
+    tape = torch.empty((max_actions, n_total, lay.token_pitch), dtype=torch.uint8, device=device)
+    slab = torch.empty((n_total, lay.game_pitch), dtype=torch.int8, device=device)
+    flags = torch.empty(n_total, dtype=torch.uint8, device=device)
+    _, _, f = env.make_synthetic_demos(hi - lo, max_actions, S, values, probs, shift, seed=seed, first_demo=lo, device=device,
+                                       tape=tape[:, lo:hi], slab=slab[lo:hi])
+    flags[lo:hi] = f
+    if ws > 1:
+        gather_shards(slab[lo:hi], n_total, dim=0, out=slab)
+        gather_shards(flags[lo:hi], n_total, dim=0, out=flags)
+        gather_shards(tape[:, lo:hi], n_total, dim=1, out=tape)
     return tape, slab, flags

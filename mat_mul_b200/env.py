@@ -8,6 +8,7 @@ on the CPU: without the CUDA library or a CUDA tensor these functions raise.
 from __future__ import annotations
 
 import ctypes as C
+from contextlib import contextmanager
 from dataclasses import dataclass
 
 import torch
@@ -35,8 +36,31 @@ def layout(S: int) -> Layout:
     return Layout(S, rp.value, gp.value, tp.value)
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+@contextmanager
+def _on(*tensors):
+    """Launch context: makes the operands' device current and yields torch's current stream OF THAT DEVICE (so a
+    launch lands where the tensors live and is ordered after their producers, whatever the caller's current
+    device is).  All operands must share one CUDA device."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        d = t.device
+        if d.type != "cuda":
+            raise TensorGameError("operands must live on a CUDA device (there is no CPU path)")
+        if dev is None:
+            dev = d
+        elif d != dev:
+            raise TensorGameError(f"operands live on different devices ({dev} and {d})")
+    with torch.cuda.device(dev):
+        yield C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _call(name: str, operands: tuple, *args) -> None:
+    """One C-ABI launch on the operands' device and that device's current torch stream (the stream is the last
+    argument of every device entry point of include/tensorgame.h)."""
+    with _on(*operands) as st:
+        check(getattr(_lib.lib(), name)(*args, st), name)
 
 
 def _need_cuda(t: torch.Tensor, name: str, dtype: torch.dtype) -> None:
@@ -76,7 +100,7 @@ def pack_states(heads: torch.Tensor, S: int | None = None, out: torch.Tensor | N
     out = new_slab(B, S, heads.device) if out is None else out
     flag = torch.zeros(1, dtype=torch.int32, device=heads.device)
     stride = heads.stride(0) if B > 1 else S ** 3
-    check(_lib.lib().tg_pack_f32(_p(heads), stride, _p(out), B, S, _p(flag), _stream()), "tg_pack_f32")
+    _call("tg_pack_f32", (heads, out, flag,), _p(heads), stride, _p(out), B, S, _p(flag))
     if int(flag.item()):
         raise TensorGameError("pack_states: residual entries must be integers in [-128, 127]")
     return out
@@ -89,18 +113,24 @@ def expand_states(slab: torch.Tensor, S: int, out: torch.Tensor | None = None) -
     if out is None:
         out = torch.empty((B, S, S, S), dtype=torch.float32, device=slab.device)
     stride = out.stride(0) if B > 1 else S ** 3
-    check(_lib.lib().tg_expand_f32(_p(slab), _p(out), stride, B, S, _stream()), "tg_expand_f32")
+    _call("tg_expand_f32", (slab, out,), _p(slab), _p(out), stride, B, S)
     return out
 
 
-def pack_actions(actions: torch.Tensor, S: int | None = None) -> torch.Tensor:
-    """int64 tokens (B, 3S) -> tape uint8 (B, TP)."""
+def pack_actions(actions: torch.Tensor, S: int | None = None, rebase: int = 0) -> torch.Tensor:
+    """int64 tokens (B, 3S) -> tape uint8 (B, TP).  rebase is added to every token first (a caller whose
+    coefficient is token - s passes rebase = 4 - s and then uses shift 4: include/tensorgame.h "Token bound");
+    tokens must land in [0, 8], the tape's alphabet."""
     _need_cuda(actions, "actions", torch.int64)
     S = S or actions.shape[-1] // 3
     B = actions.shape[0]
+    if rebase:
+        actions = actions + rebase
+    if B and (int(actions.min()) < 0 or int(actions.max()) > 8):
+        raise TensorGameError("pack_actions: factor coefficients must be in [-4, 4] (tape tokens in [0, 8])")
     tape = torch.empty((B, layout(S).token_pitch), dtype=torch.uint8, device=actions.device)
     flag = torch.zeros(1, dtype=torch.int32, device=actions.device)
-    check(_lib.lib().tg_pack_actions_i64(_p(actions), _p(tape), B, S, _p(flag), _stream()), "tg_pack_actions_i64")
+    _call("tg_pack_actions_i64", (actions, tape, flag,), _p(actions), _p(tape), B, S, _p(flag))
     if int(flag.item()):
         raise TensorGameError("pack_actions: tokens must be in [0, 255]")
     return tape
@@ -110,7 +140,7 @@ def unpack_actions(tape: torch.Tensor, S: int) -> torch.Tensor:
     _need_cuda(tape, "tape", torch.uint8)
     B = tape.shape[0]
     out = torch.empty((B, 3 * S), dtype=torch.int64, device=tape.device)
-    check(_lib.lib().tg_unpack_actions_i64(_p(tape), _p(out), B, S, _stream()), "tg_unpack_actions_i64")
+    _call("tg_unpack_actions_i64", (tape, out,), _p(tape), _p(out), B, S)
     return out
 
 
@@ -131,7 +161,7 @@ def step_batch(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: 
     out = torch.empty_like(slab) if out is None else out
     flags = torch.empty(B, dtype=torch.uint8, device=slab.device) if flags is None else flags
     nnz = torch.empty(B, dtype=torch.int32, device=slab.device) if nnz is None else nnz
-    check(_lib.lib().tg_step(_p(slab), _p(tape), _p(out), _p(flags), _p(nnz), B, S, shift, _stream()), "tg_step")
+    _call("tg_step", (slab, tape, out, flags, nnz,), _p(slab), _p(tape), _p(out), _p(flags), _p(nnz), B, S, shift)
     return out, flags, nnz
 
 
@@ -154,8 +184,7 @@ def expand_children(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, 
     flags = torch.empty((B, k), dtype=torch.uint8, device=dev)
     nnz = torch.empty((B, k), dtype=torch.int32, device=dev)
     keys = torch.empty((B, k), dtype=torch.int64, device=dev) if with_keys else None
-    check(_lib.lib().tg_expand_children(_p(slab), _p(tape), k, _p(children), _p(flags), _p(nnz), _p(keys), B, S, shift,
-                                        _stream()), "tg_expand_children")
+    _call("tg_expand_children", (slab, tape, children, flags, nnz, keys,), _p(slab), _p(tape), k, _p(children), _p(flags), _p(nnz), _p(keys), B, S, shift)
     return children, flags, nnz, keys
 
 
@@ -173,8 +202,7 @@ def rollout(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: tor
     flags = torch.empty(B, dtype=torch.uint8, device=slab.device)
     nnz = torch.empty(B, dtype=torch.int32, device=slab.device)
     steps = torch.empty(B, dtype=torch.int32, device=slab.device)
-    check(_lib.lib().tg_rollout(_p(slab), _p(tape), B * lay.token_pitch, K, _p(out), _p(flags), _p(nnz), _p(steps), B, S, shift,
-                                _stream()), "tg_rollout")
+    _call("tg_rollout", (slab, tape, out, flags, nnz, steps,), _p(slab), _p(tape), B * lay.token_pitch, K, _p(out), _p(flags), _p(nnz), _p(steps), B, S, shift)
     return out, flags, nnz, steps
 
 
@@ -189,8 +217,7 @@ def replay(slab: torch.Tensor, tape: torch.Tensor, S: int, shift: int, out: torc
     out = torch.empty_like(slab) if out is None else out
     flags = torch.empty(B, dtype=torch.uint8, device=slab.device)
     nnz = torch.empty(B, dtype=torch.int32, device=slab.device)
-    check(_lib.lib().tg_replay(_p(slab), _p(tape), B * lay.token_pitch, K, _p(out), _p(flags), _p(nnz), B, S, shift, _stream()),
-          "tg_replay")
+    _call("tg_replay", (slab, tape, out, flags, nnz,), _p(slab), _p(tape), B * lay.token_pitch, K, _p(out), _p(flags), _p(nnz), B, S, shift)
     return out, flags, nnz
 
 
@@ -225,9 +252,8 @@ def make_synthetic_demos(n_demos: int, max_actions: int, S: int, values=(-1, 0, 
     flags = torch.empty(n_demos, dtype=torch.uint8, device=dev)
     stride = tape.stride(0) if max_actions > 1 else n_demos * lay.token_pitch
     with torch.cuda.device(dev):
-        check(_lib.lib().tg_demo_gen_philox(seed, first_demo, n_demos, max_actions, S, shift, v.ctypes.data, p.ctypes.data,
-                                            len(v), max_tries, _p(tape), stride, _p(slab), _p(flags), _stream()),
-              "tg_demo_gen_philox")
+        _call("tg_demo_gen_philox", (tape, slab, flags,), seed, first_demo, n_demos, max_actions, S, shift, v.ctypes.data, p.ctypes.data,
+                                            len(v), max_tries, _p(tape), stride, _p(slab), _p(flags))
     return tape, slab, flags
 
 
@@ -241,8 +267,7 @@ def accumulate_demos(tape: torch.Tensor, S: int, shift: int, slab: torch.Tensor 
     if slab is None:
         slab = torch.empty((N, lay.game_pitch), dtype=torch.int8, device=tape.device)
     flags = torch.empty(N, dtype=torch.uint8, device=tape.device)
-    check(_lib.lib().tg_demo_accumulate(_p(tape), N * lay.token_pitch, N, R, S, shift, _p(slab), _p(flags), _stream()),
-          "tg_demo_accumulate")
+    _call("tg_demo_accumulate", (tape, slab, flags,), _p(tape), N * lay.token_pitch, N, R, S, shift, _p(slab), _p(flags))
     return slab, flags
 
 
@@ -285,9 +310,9 @@ def demos_from_ustream(ustream, n_demos: int, max_actions: int, S: int, values, 
     ws_bytes = int(_lib.lib().tg_demo_from_ustream_workspace(n_u, S))
     ws = torch.empty(ws_bytes + 16, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.lib().tg_demo_from_ustream(_p(u), n_u, v.ctypes.data, p.ctypes.data, len(v), max_actions, S, shift, n_demos,
+        _call("tg_demo_from_ustream", (u, tape, slab, flags, result, ws,), _p(u), n_u, v.ctypes.data, p.ctypes.data, len(v), max_actions, S, shift, n_demos,
                                               _p(tape), n_demos * lay.token_pitch, _p(slab), _p(flags), _p(result), _p(ws),
-                                              ws_bytes, _stream()), "tg_demo_from_ustream")
+                                              ws_bytes)
     done, consumed = (int(x) for x in result.tolist())
     return tape, slab, flags, done, consumed
 
@@ -329,8 +354,7 @@ def accumulate_demos_tc(tape: torch.Tensor, shift: int, slab: torch.Tensor | Non
     if slab is None:
         slab = torch.empty((N, lay.game_pitch), dtype=torch.int8, device=tape.device)
     flags = torch.empty(N, dtype=torch.uint8, device=tape.device)
-    check(_lib.lib().tg_demo_accumulate_tc(_p(tape), N * lay.token_pitch, N, R, 16, shift, _p(slab), _p(flags), _stream()),
-          "tg_demo_accumulate_tc")
+    _call("tg_demo_accumulate_tc", (tape, slab, flags,), _p(tape), N * lay.token_pitch, N, R, 16, shift, _p(slab), _p(flags))
     return slab, flags
 
 
@@ -349,8 +373,8 @@ def demo_samples(tape: torch.Tensor, slab: torch.Tensor, idx: torch.Tensor, S: i
     scalars = torch.empty((nb, 1), dtype=torch.float32, device=dev)
     actions = torch.empty((nb, 3 * S), dtype=torch.int64, device=dev)
     rewards = torch.empty((nb, 1), dtype=torch.float32, device=dev)
-    check(_lib.lib().tg_demo_sample(_p(tape), N * lay.token_pitch, _p(slab), N, R, S, dim_t, replay_shift, _p(idx), nb,
-                                    _p(states), _p(scalars), _p(actions), _p(rewards), _stream()), "tg_demo_sample")
+    _call("tg_demo_sample", (tape, slab, idx, states, scalars, actions, rewards,), _p(tape), N * lay.token_pitch, _p(slab), N, R, S, dim_t, replay_shift, _p(idx), nb,
+                                    _p(states), _p(scalars), _p(actions), _p(rewards))
     return states, scalars, actions, rewards
 
 
@@ -358,7 +382,7 @@ def slice_rank(slab: torch.Tensor, S: int) -> torch.Tensor:
     """get_rank per game (utils.py:134-140): int32 (B,)."""
     _need_cuda(slab, "slab", torch.int8)
     ranks = torch.empty(slab.shape[0], dtype=torch.int32, device=slab.device)
-    check(_lib.lib().tg_slice_rank(_p(slab), _p(ranks), slab.shape[0], S, _stream()), "tg_slice_rank")
+    _call("tg_slice_rank", (slab, ranks,), _p(slab), _p(ranks), slab.shape[0], S)
     return ranks
 
 
@@ -366,7 +390,7 @@ def state_keys(slab: torch.Tensor, S: int) -> torch.Tensor:
     """64-bit state keys (as int64 bit patterns), replacing utils.state_to_str dict keys."""
     _need_cuda(slab, "slab", torch.int8)
     keys = torch.empty(slab.shape[0], dtype=torch.int64, device=slab.device)
-    check(_lib.lib().tg_state_key(_p(slab), _p(keys), slab.shape[0], S, _stream()), "tg_state_key")
+    _call("tg_state_key", (slab, keys,), _p(slab), _p(keys), slab.shape[0], S)
     return keys
 
 
@@ -378,7 +402,7 @@ def sample_unimodular(n: int, S: int, seed: int = 0, first: int = 0, p_nonzero: 
         raise TensorGameError("sample_unimodular needs a CUDA device (there is no CPU path)")
     mats = torch.empty((n, 3, S, S), dtype=torch.int8, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.lib().tg_sample_unimodular(seed, first, n, S, float(p_nonzero), _p(mats), _stream()), "tg_sample_unimodular")
+        _call("tg_sample_unimodular", (mats,), seed, first, n, S, float(p_nonzero), _p(mats))
     return mats
 
 
@@ -397,7 +421,7 @@ def change_of_basis(slab: torch.Tensor, mats: torch.Tensor, S: int, tape: torch.
     per_game = int(m.shape[0] == N and N > 1)
     out = torch.empty_like(slab)
     flags = torch.zeros(N, dtype=torch.uint8, device=slab.device)
-    check(_lib.lib().tg_change_of_basis(_p(slab), _p(m), per_game, _p(out), _p(flags), N, S, _stream()), "tg_change_of_basis")
+    _call("tg_change_of_basis", (slab, m, out, flags,), _p(slab), _p(m), per_game, _p(out), _p(flags), N, S)
     if tape is None:
         return out, flags
     _need_cuda(tape, "tape", torch.uint8)
@@ -405,9 +429,8 @@ def change_of_basis(slab: torch.Tensor, mats: torch.Tensor, S: int, tape: torch.
     R = tape.shape[0]
     shift_out = shift if shift_out is None else shift_out
     tape_out = torch.empty_like(tape)
-    check(_lib.lib().tg_change_of_basis_factors(_p(tape), N * lay.token_pitch, shift, _p(m), per_game, _p(tape_out),
-                                                N * lay.token_pitch, shift_out, _p(flags), N, R, S, _stream()),
-          "tg_change_of_basis_factors")
+    _call("tg_change_of_basis_factors", (tape, m, tape_out, flags,), _p(tape), N * lay.token_pitch, shift, _p(m), per_game, _p(tape_out),
+                                                N * lay.token_pitch, shift_out, _p(flags), N, R, S)
     return out, tape_out, flags
 
 
@@ -450,6 +473,27 @@ class HostStepper:
                 raise TensorGameError("HostStepper takes contiguous CPU tensors")
         B = slab.shape[0]
         check(_lib.lib().tg_step_host(self._ctx, _p(slab), _p(tape), _p(out), _p(flags), _p(nnz), B, shift), "tg_step_host")
+
+    def rollout(self, slab: torch.Tensor, tape: torch.Tensor, out: torch.Tensor, flags: torch.Tensor, nnz: torch.Tensor,
+                steps: torch.Tensor, shift: int) -> None:
+        """K fused steps per PCIe round trip (tg_rollout_host): tape is the dense step-major CPU tape (K, B, TP)."""
+        for t in (slab, tape, out, flags, nnz, steps):
+            if t.is_cuda or not t.is_contiguous():
+                raise TensorGameError("HostStepper takes contiguous CPU tensors")
+        K, B = tape.shape[0], slab.shape[0]
+        check(_lib.lib().tg_rollout_host(self._ctx, _p(slab), _p(tape), K, _p(out), _p(flags), _p(nnz), _p(steps), B, shift),
+              "tg_rollout_host")
+
+    def make_demos(self, tape: torch.Tensor, slab: torch.Tensor, flags: torch.Tensor, shift: int, values, probs, seed: int = 0,
+                   first_demo: int = 0, max_tries: int = 64) -> None:
+        """Synthetic demonstrations straight into CPU buffers (tg_demo_gen_host): tape (R, N, TP), slab (N, GP), flags (N,)."""
+        for t in (tape, slab, flags):
+            if t.is_cuda or not t.is_contiguous():
+                raise TensorGameError("HostStepper takes contiguous CPU tensors")
+        v, p = _cat_arrays(values, probs)
+        R, N = tape.shape[0], tape.shape[1]
+        check(_lib.lib().tg_demo_gen_host(self._ctx, seed, first_demo, N, R, shift, v.ctypes.data, p.ctypes.data, len(v), max_tries,
+                                          _p(tape), _p(slab), _p(flags)), "tg_demo_gen_host")
 
     def close(self) -> None:
         if self._ctx:

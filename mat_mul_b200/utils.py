@@ -42,6 +42,7 @@ class ChildStates(list):
     """The list get_child_states returns, carrying what the step kernel already knows about every child."""
 
     parent = None       # the state tensor the children were expanded from
+    range_flags = None  # bool (k,): the child left the int8 slab's guaranteed zone (always False: expansion raises)
     null_flags = None   # bool (k,): child head == parent head (utils.py:191-194)
     terminal = None     # bool (k,): child head all zero
     nnz = None          # int32 (k,)

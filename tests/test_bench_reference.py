@@ -17,7 +17,10 @@ def test_reference_arm_prints_contract_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"] == "env_steps_per_sec" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    have_ref = (ROOT / "baseline" / "_ref" / "utils.py").exists()
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["port"]["kind"] == "port" and line["port"]["value"] > 0  # the C/OpenMP port is always reported beside it
+    assert set(line["config"]) == {"workload", "games_per_gpu", "size", "shift", "sharding", "l2"}
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 
 

@@ -41,6 +41,13 @@ def _worker(rank: int, ws: int, port: int, n_total: int):
         want = torch.arange(n_total)
         assert full_tape.shape == (R, n_total, TP) and torch.equal(full_tape[1, :, 5], (want % 251).to(torch.uint8))
         assert full_slab.shape == (n_total, GP) and torch.equal(full_slab[:, 7], (want % 100).to(torch.int8))
+        if n_total % ws == 0:  # equal shards: gathered in place, the shard being the rank's slice of the output
+            out_slab = torch.zeros((n_total, GP), dtype=torch.int8)
+            out_slab[lo:hi] = slab
+            assert tgd.gather_shards(out_slab[lo:hi], n_total, dim=0, out=out_slab) is out_slab and torch.equal(out_slab, full_slab)
+            out_tape = torch.zeros((R, n_total, TP), dtype=torch.uint8)
+            out_tape[:, lo:hi] = tape
+            assert tgd.gather_shards(out_tape[:, lo:hi], n_total, dim=1, out=out_tape) is out_tape and torch.equal(out_tape, full_tape)
         # statistics: game i is solved iff i % 3 == 0, nnz = i + 5, steps = i % 7, range flag iff i % 10 == 0
         flags = ((idx % 3 == 0).to(torch.uint8) * 1) | ((idx % 10 == 0).to(torch.uint8) * 4)
         st = tgd.reduce_episode_stats(flags, (idx + 5).to(torch.int32), (idx % 7).to(torch.int32))
