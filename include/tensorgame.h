@@ -61,6 +61,8 @@ extern "C" {
 #define TG_FLAG_RANGE 4u    /* a residual entry left [-64, 63] (int8 slab no longer guaranteed) or a token exceeded 2*shift */
 #define TG_FLAG_EXHAUSTED 8u /* demo generation: a term hit max_tries and was forced to a unit triple */
 #define TG_FLAG_TOKEN_RANGE 16u /* change of basis: a transformed factor entry left [-shift_out, shift_out] */
+#define TG_FLAG_PATH_PLANES 32u /* change of basis, informational: 16x16x16 game computed on int8 byte planes (not f16) */
+#define TG_FLAG_PATH_EXACT 64u  /* change of basis, informational: game computed by the exact int32 kernel (no fast path held it) */
 
 int tg_version(void);
 int tg_last_cuda_error(void);
@@ -81,6 +83,9 @@ int tg_pack_f32(const float *src, int64_t src_stride, int8_t *slab, int64_t B, i
  * allows). */
 int tg_expand_f32(const int8_t *slab, float *dst, int64_t dst_stride, int64_t B, int S, void *stream);
 /* int64 tokens (B,3S) (reference action format, utils.py:56-66) <-> tape */
+/* the same two conversions for int16 slabs (range: integers in [-32768, 32767]) */
+int tg_pack_f32_i16(const float *src, int64_t src_stride, int16_t *slab16, int64_t B, int S, int32_t *range_flag, void *stream);
+int tg_expand_f32_i16(const int16_t *slab16, float *dst, int64_t dst_stride, int64_t B, int S, void *stream);
 int tg_pack_actions_i64(const int64_t *actions, uint8_t *tape, int64_t B, int S, int32_t *range_flag, void *stream);
 int tg_unpack_actions_i64(const uint8_t *tape, int64_t *actions, int64_t B, int S, void *stream);
 
@@ -142,6 +147,11 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
  * list (utils.py:40-53 uvw_to_demo, utils.py:232, datasets.py:141). */
 int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,
                        uint8_t *flags, void *stream);
+/* the same sum into an int16 slab [N][GP] of int16 (plain int32 arithmetic per entry: exact for every tape and any
+ * shift in [0,127]; TG_FLAG_RANGE = an entry does not fit int16).  The reference accumulates targets in float32
+ * without limit (utils.py:218-232); this is where targets beyond the int8 slab's zone go. */
+int tg_demo_accumulate_i16(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int16_t *slab16,
+                           uint8_t *flags, void *stream);
 /* For S = 16 and R <= 64 tg_demo_accumulate and tg_demo_gen_philox sum the targets on the tensor cores
  * (mma.sync f16, exact integer arithmetic; csrc/tg_demo_mma.cu) -- same results.
  * tg_demo_accumulate_tc: the same sum with tcgen05.mma kind::i8 (int32 accumulators in TMEM), an experimental entry
@@ -177,6 +187,19 @@ int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *
                    int replay_shift, const int64_t *idx, int64_t nb, float *states, float *scalars, int64_t *actions,
                    float *rewards, void *stream);
 
+/* The same samples from a DEMO-MAJOR store: action records uint8 [N][R][TP] (tg_tape_to_demo_major of a step-major tape;
+ * the records a .. R-1 a sample needs are one contiguous run) and targets as an int8 slab (targets_i16 == 0) or an int16
+ * slab [N][GP] of int16 (targets_i16 != 0; entry (i,j,k) at element i*RP + j*S + k -- the format targets beyond int8
+ * are kept in, tg_demo_accumulate_i16).  target_bound >= max |target entry| (127 for an int8 slab) selects the packed
+ * 16-bit arithmetic when target_bound + R * cmax^3 fits an int16.  Inputs and outputs move by TMA bulk copies; states may
+ * start at any float (16-byte aligned batches leave with one bulk store per CTA).  Samples whose index is out of range
+ * get all-zero states (scalars / actions / rewards untouched). */
+int tg_demo_sample_dm(const uint8_t *tape_dm, const void *targets, int targets_i16, int target_bound, int64_t N, int R, int S,
+                      int dim_t, int replay_shift, const int64_t *idx, int64_t nb, float *states, float *scalars, int64_t *actions,
+                      float *rewards, void *stream);
+/* step-major tape uint8 [R][N][TP] (byte stride tape_step_stride between steps) -> demo-major records uint8 [N][R][TP] */
+int tg_tape_to_demo_major(const uint8_t *tape, int64_t tape_step_stride, uint8_t *tape_dm, int64_t N, int R, int S, void *stream);
+
 /* ---- K6: rank reward ------------------------------------------------------ */
 /* ranks[b] = sum_i rank(T_b[i,:,:]) -- get_rank (utils.py:134-140), the
  * terminal reward -get_rank of act.py:59,214.  Exact rank over GF(2^31-1)
@@ -198,6 +221,12 @@ int tg_state_key(const int8_t *slab, uint64_t *keys, int64_t B, int S, void *str
  * int8 slab's guaranteed zone; intermediates are int32 and exact). */
 int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, int8_t *slab_out, uint8_t *flags, int64_t N,
                        int S, void *stream);
+/* The same contraction with the result as an int16 slab [N][GP] of int16 (entry (i,j,k) at element i*RP + j*S + k) --
+ * SURVEY 8(d)'s format "int8 in, int16 out": unimodular matrices with off-diagonal density 0.3 take 16x16x16 residuals to
+ * |T'| ~ 1000.  TG_FLAG_RANGE here means an entry does not fit int16.  The informational bits TG_FLAG_PATH_* say which
+ * kernel computed each game (both entry points). */
+int tg_change_of_basis_i16(const int8_t *slab_in, const int8_t *mats, int per_game, int16_t *slab16_out, uint8_t *flags, int64_t N,
+                           int S, void *stream);
 /* factors follow: u' = A u, v' = B v, w' = C w for every step of a step-major
  * tape; token' = coef' + shift_out.  ORs TG_FLAG_TOKEN_RANGE into flags[n] if a
  * transformed entry leaves [-shift_out, shift_out] (flags must be initialised). */

@@ -231,6 +231,256 @@ __global__ void __launch_bounds__(128, PACK16 ? (S == 16 ? 6 : 8) : 1)
     for (int q = L.c; q < 3 * S; q += G::WR) actions[b * 3 * S + q] = (long long)ta[q];
 }
 
+// ------------------------------------------------------------------ K4, demo-major store
+// The same samples from the DEMO-MAJOR store: action records uint8 [N][R][TP] (the records a .. R-1 a sample needs are one
+// contiguous run of HBM) and targets as an int8 slab [N][GP] or an int16 slab [N][GP] (entry (i,j,k) at element
+// i*RP + j*S + k, two bytes each).  Every byte a CTA reads or writes moves by TMA:
+//   in:  per sample one bulk copy of its records a .. R-1 and one of its target, completion on one mbarrier;
+//   out: the CTA builds the float32 states of its SPC samples in shared memory as the exact image of their (contiguous)
+//        region of the states array, which leaves with ONE bulk store (a cooperative scalar copy when the region is not
+//        16-byte aligned / sized: odd tails, caller buffers at odd offsets).
+// In between, thread (sample, word column c) replays the later actions on packed 16-bit lanes exactly as above.  The rows
+// of 9x9x9 (81 floats) are not 16-byte aligned in that image, so a thread stores its four floats of a row one by one; to
+// keep those stores free of bank conflicts, a thread holds its four entries ROTATED by (c >> 3) & 3 -- position q of
+// thread c is entry (q + (c >> 3)) & 3 of its word column, a per-thread constant baked into the offsets it reads its w
+// coefficients and target bytes from -- so that lanes c, c + 8, c + 16 (same bank for the same entry) store different
+// entries in the same instruction.
+template <int S>
+struct SampleCfg {
+    using G = Geo<S>;
+    static constexpr int SPC = S == 4 ? 32 : (S == 9 ? 4 : 2);       // samples per CTA: SPC * dim_t * S^3 * 4 bytes is a multiple of 16
+    static constexpr int NT = ((SPC * G::WR + 31) / 32) * 32;         // 128 / 96 / 128
+    static __host__ __device__ constexpr long long smem_bytes(int R, int dim_t, bool tgt16) {
+        return (((long long)SPC * dim_t * G::S3 * 4 + 15) & ~15LL) + (long long)SPC * R * G::TP + (long long)SPC * G::GP * (tgt16 ? 2 : 1) +
+               ((SPC * 4 + 15) & ~15) + 16;
+    }
+};
+
+// sign-extended 16-bit entry e (0..3) of the pair of words (w0 = entries 0,1; w1 = entries 2,3): one PRMT, selector in a register
+__device__ __forceinline__ int sext_half_sel(uint32_t w0, uint32_t w1, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w0), "r"(w1), "r"(sel));
+    return (int)d;
+}
+
+template <int S, bool TGT16, bool PACK16>
+__global__ void __launch_bounds__(SampleCfg<S>::NT)
+    demo_sample_dm_kernel(const uint8_t *__restrict__ tape_dm, const uint8_t *__restrict__ targets, long long N, int R, int dim_t,
+                          int replay_shift, const long long *__restrict__ idx, long long nb, float *__restrict__ states,
+                          float *__restrict__ scalars, long long *__restrict__ actions, float *__restrict__ rewards) {
+    using G = Geo<S>;
+    using C = SampleCfg<S>;
+    constexpr int SPC = C::SPC, NT = C::NT, GPB = G::GP * (TGT16 ? 2 : 1);
+    extern __shared__ __align__(128) uint8_t smem[];
+    float *s_tile = reinterpret_cast<float *>(smem);                                   // [SPC][dim_t][S^3]
+    uint8_t *s_rec = smem + (((size_t)SPC * dim_t * G::S3 * 4 + 15) & ~(size_t)15);   // [SPC][R][TP]
+    uint8_t *s_tgt = s_rec + (size_t)SPC * R * G::TP;                                  // [SPC][GPB]
+    int *s_a = reinterpret_cast<int *>(s_tgt + (size_t)SPC * GPB);                     // [SPC] action index, -1 = bad sample
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_a) + ((SPC * 4 + 15) & ~15));
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * SPC;
+    const int ns = (int)min((long long)SPC, nb - b0);
+    if (tid == 0) {
+        mbar_init(s_bar, (uint32_t)ns);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid < ns) {
+        const long long id = idx[b0 + tid];
+        long long demo = -1;
+        int a = 0;
+        if (id >= 0) split_index(id, R, demo, a);
+        const bool ok = demo >= 0 && demo < N;
+        s_a[tid] = ok ? a : -1;
+        if (ok) {
+            const uint32_t rb = (uint32_t)(R - a) * G::TP;
+            mbar_expect_tx(s_bar, rb + (uint32_t)GPB);
+            bulk_g2s(s_rec + ((size_t)tid * R + a) * G::TP, tape_dm + ((size_t)demo * R + a) * G::TP, rb, s_bar);
+            bulk_g2s(s_tgt + (size_t)tid * GPB, targets + (size_t)demo * GPB, (uint32_t)GPB, s_bar);
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(s_bar)) : "memory");
+        }
+    }
+    __syncthreads(); // s_a
+    mbar_wait(s_bar, 0);
+    // the records that are only replayed (j > a) become int8 coefficients in place (token - replay_shift; no borrow between
+    // bytes: token | 0x80 > shift), so the replay loop has no subtraction per byte
+    {
+        const uint32_t sh4 = (uint32_t)replay_shift * ONES4;
+        for (int sl = 0; sl < ns; sl++) {
+            const int a = s_a[sl];
+            if (a < 0) continue;
+            uint32_t *rw = reinterpret_cast<uint32_t *>(s_rec + ((size_t)sl * R + a + 1) * G::TP);
+            for (int w = tid; w < (R - a - 1) * (G::TP / 4); w += NT) rw[w] = ((rw[w] | H4) - sh4) ^ H4;
+        }
+    }
+    __syncthreads();
+
+    const int sl = tid / G::WR;
+    const bool worker = tid < SPC * G::WR && sl < ns;
+    if (worker) {
+        Lane<S> L;
+        L.init(tid % G::WR);
+        const int a = s_a[sl];
+        const long long b = b0 + sl;
+        float *st = s_tile + (size_t)sl * dim_t * G::S3;
+        const int nv = min(4, G::S2 - 4 * L.c); // entries of this word column inside a row
+        // position q of this thread is entry ord(q) = (q + rot) & 3 of its word column (rot = 0 unless the rows are unaligned)
+        const int rot = (G::S2 % 4 != 0) ? ((L.c >> 3) & 3) : 0;
+        int offw[4], wpos[4];
+        bool inA[4], valid[4];
+        uint32_t tsel[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = (q + rot) & 3;
+            offw[q] = L.off_w[0], inA[q] = true;
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                if (x == e) offw[q] = L.off_w[x], inA[q] = !G::STRADDLE || ((L.maskA >> (8 * x)) & 1u);
+            valid[q] = e < nv;
+            wpos[q] = 4 * L.c + e;
+            // target entry e as a sign-extended int: int8 slab -> byte e of the word; int16 slab -> half e of the word pair
+            tsel[q] = TGT16 ? ((uint32_t)(2 * e) | ((uint32_t)(2 * e + 1) << 4) | ((uint32_t)(8 | (2 * e + 1)) << 8) | ((uint32_t)(8 | (2 * e + 1)) << 12))
+                            : ((uint32_t)e | ((uint32_t)(8 | e) << 4) | ((uint32_t)(8 | e) << 8) | ((uint32_t)(8 | e) << 12));
+        }
+        auto put4 = [&](float *row, float f0, float f1, float f2, float f3) {
+            if constexpr (G::S2 % 4 == 0) {
+                *reinterpret_cast<float4 *>(row + 4 * L.c) = make_float4(f0, f1, f2, f3);
+            } else {
+                if (valid[0]) row[wpos[0]] = f0;
+                if (valid[1]) row[wpos[1]] = f1;
+                if (valid[2]) row[wpos[2]] = f2;
+                if (valid[3]) row[wpos[3]] = f3;
+            }
+        };
+        if (a < 0) {
+            for (int s = 0; s < dim_t; s++)
+#pragma unroll
+                for (int i = 0; i < S; i++) put4(st + (size_t)s * G::S3 + i * G::S2, 0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int8_t *rec0 = reinterpret_cast<const int8_t *>(s_rec + (size_t)sl * R * G::TP);
+            const uint8_t *tg = s_tgt + (size_t)sl * GPB;
+            // ---- head = target - sum of the later actions
+            int acc[S][PACK16 ? 2 : 4];
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                uint32_t w0, w1 = 0;
+                if constexpr (TGT16) {
+                    const uint2 p = *reinterpret_cast<const uint2 *>(tg + (size_t)(i * G::RP + 4 * L.c) * 2);
+                    w0 = p.x, w1 = p.y;
+                } else {
+                    w0 = *reinterpret_cast<const uint32_t *>(tg + i * G::RP + 4 * L.c);
+                }
+                const int e0 = sext_half_sel(w0, w1, tsel[0]), e1 = sext_half_sel(w0, w1, tsel[1]), e2 = sext_half_sel(w0, w1, tsel[2]),
+                          e3 = sext_half_sel(w0, w1, tsel[3]);
+                if constexpr (PACK16) {
+                    acc[i][0] = e0 + e1 * 65536, acc[i][1] = e2 + e3 * 65536;
+                } else {
+                    acc[i][0] = e0, acc[i][1] = e1, acc[i][2] = e2, acc[i][3] = e3;
+                }
+            }
+            const int8_t *rec = rec0 + (size_t)(a + 1) * G::TP;
+#pragma unroll 2
+            for (int j = a + 1; j < R; j++, rec += G::TP) {
+                const int nvA = -(int)rec[L.off_vA], nvB = G::STRADDLE ? -(int)rec[L.off_vB] : nvA;
+                const int p0 = (inA[0] ? nvA : nvB) * (int)rec[offw[0]], p1 = (inA[1] ? nvA : nvB) * (int)rec[offw[1]],
+                          p2 = (inA[2] ? nvA : nvB) * (int)rec[offw[2]], p3 = (inA[3] ? nvA : nvB) * (int)rec[offw[3]];
+                uint32_t uq[4];
+                if constexpr (S <= 4) {
+                    uq[0] = *reinterpret_cast<const uint32_t *>(rec);
+                } else {
+                    const uint4 q4 = *reinterpret_cast<const uint4 *>(rec);
+                    uq[0] = q4.x, uq[1] = q4.y, uq[2] = q4.z, uq[3] = q4.w;
+                }
+                const int np0 = p0 + p1 * 65536, np1 = p2 + p3 * 65536;
+#pragma unroll
+                for (int i = 0; i < S; i++) {
+                    int u;
+                    switch (i & 3) {
+                    case 0: u = sext_byte<0>(uq[i >> 2]); break;
+                    case 1: u = sext_byte<1>(uq[i >> 2]); break;
+                    case 2: u = sext_byte<2>(uq[i >> 2]); break;
+                    default: u = sext_byte<3>(uq[i >> 2]); break;
+                    }
+                    if constexpr (PACK16) {
+                        acc[i][0] += u * np0, acc[i][1] += u * np1;
+                    } else {
+                        acc[i][0] += u * p0, acc[i][1] += u * p1, acc[i][2] += u * p2, acc[i][3] += u * p3;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                float f[4];
+                if constexpr (PACK16) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int x = acc[i][h];
+                        const int lo = (int)(short)(x & 0xFFFF);
+                        f[2 * h] = (float)lo, f[2 * h + 1] = (float)((x - lo) >> 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) f[q] = (float)acc[i][q];
+                }
+                put4(st + i * G::S2, f[0], f[1], f[2], f[3]);
+            }
+            // ---- history slots: rank-1 tensors of the next actions, latest first
+            const int hi = min(a + dim_t, R);
+            for (int s = 1; s < dim_t; s++) {
+                const int j = hi - s;
+                float *ss = st + (size_t)s * G::S3;
+                if (j >= a + 1) {
+                    const int8_t *hr = rec0 + (size_t)j * G::TP;
+                    const int vA = (int)hr[L.off_vA], vB = G::STRADDLE ? (int)hr[L.off_vB] : vA;
+                    const float pf0 = (float)((inA[0] ? vA : vB) * (int)hr[offw[0]]), pf1 = (float)((inA[1] ? vA : vB) * (int)hr[offw[1]]),
+                                pf2 = (float)((inA[2] ? vA : vB) * (int)hr[offw[2]]), pf3 = (float)((inA[3] ? vA : vB) * (int)hr[offw[3]]);
+#pragma unroll
+                    for (int i = 0; i < S; i++) {
+                        const float uf = (float)(int)hr[i];
+                        put4(ss + i * G::S2, uf * pf0, uf * pf1, uf * pf2, uf * pf3);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < S; i++) put4(ss + i * G::S2, 0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (L.c == 0) {
+                scalars[b] = (float)(R - a);
+                rewards[b] = -(float)(a + 1);
+            }
+            const uint8_t *ta = s_rec + ((size_t)sl * R + a) * G::TP; // the sample's own action: raw tokens
+            for (int q = L.c; q < 3 * S; q += G::WR) actions[b * 3 * S + q] = (long long)ta[q];
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    float *dst = states + b0 * (long long)dim_t * G::S3;
+    const size_t bytes = (size_t)ns * dim_t * G::S3 * 4;
+    if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (tid == 0) {
+            bulk_s2g(dst, s_tile, (uint32_t)bytes);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else {
+        for (size_t e = tid; e < bytes / 4; e += NT) dst[e] = s_tile[e];
+    }
+}
+
+// step-major tape [R][N][TP] -> demo-major records [N][R][TP], 16 bytes per thread
+__global__ void tape_to_demo_major_kernel(const uint4 *__restrict__ src, long long src_step_stride16, uint4 *__restrict__ dst,
+                                          long long N, int R, int tp16) {
+    const long long total = N * R * tp16;
+    for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(x % tp16);
+        const long long nr = x / tp16;
+        const int r = (int)(nr % R);
+        const long long n = nr / R;
+        dst[x] = __ldg(src + (size_t)r * src_step_stride16 + n * tp16 + w);
+    }
+}
+
 // ------------------------------------------------------------------ K6
 // get_rank (utils.py:134-140): sum over the S slices T[i,:,:] of the matrix
 // rank.  The reference takes a float32 SVD; here the rank is computed exactly
@@ -383,6 +633,30 @@ static int launch_demo_sample(const uint8_t *tape, long long tape_step_stride, c
 #undef TG_ARGS
 }
 
+template <int S, bool T16, bool P16>
+static int launch_demo_sample_dm_variant(const uint8_t *tape_dm, const uint8_t *targets, long long N, int R, int dim_t, int replay_shift,
+                                         const long long *idx, long long nb, float *states, float *scalars, long long *actions,
+                                         float *rewards, cudaStream_t st) {
+    using C = SampleCfg<S>;
+    const long long smem = C::smem_bytes(R, dim_t, T16);
+    if (smem > 227 * 1024) return TG_E_ARG;
+    const unsigned grid = (unsigned)((nb + C::SPC - 1) / C::SPC);
+    auto kern = demo_sample_dm_kernel<S, T16, P16>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, C::NT, (size_t)smem, st>>>(tape_dm, targets, N, R, dim_t, replay_shift, idx, nb, states, scalars, actions, rewards);
+    return TG_OK;
+}
+
+template <int S>
+static int launch_demo_sample_dm(const uint8_t *tape_dm, const uint8_t *targets, bool t16, bool p16, long long N, int R, int dim_t,
+                                 int replay_shift, const long long *idx, long long nb, float *states, float *scalars,
+                                 long long *actions, float *rewards, cudaStream_t st) {
+#define TG_ARGS tape_dm, targets, N, R, dim_t, replay_shift, idx, nb, states, scalars, actions, rewards, st
+    if (t16) return p16 ? launch_demo_sample_dm_variant<S, true, true>(TG_ARGS) : launch_demo_sample_dm_variant<S, true, false>(TG_ARGS);
+    return p16 ? launch_demo_sample_dm_variant<S, false, true>(TG_ARGS) : launch_demo_sample_dm_variant<S, false, false>(TG_ARGS);
+#undef TG_ARGS
+}
+
 } // namespace tg
 
 extern "C" {
@@ -403,6 +677,42 @@ int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *
                                                   states, scalars, (long long *)actions, rewards, pack16, st);
         if (rc != TG_OK) return rc;
     });
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_demo_sample_dm(const uint8_t *tape_dm, const void *targets, int targets_i16, int target_bound, int64_t N, int R, int S,
+                      int dim_t, int replay_shift, const int64_t *idx, int64_t nb, float *states, float *scalars, int64_t *actions,
+                      float *rewards, void *stream) {
+    if (!tg::supported_S(S) || N < 0 || R < 1 || dim_t < 1 || nb < 0 || target_bound < 0) return TG_E_ARG;
+    if (nb == 0) return TG_OK;
+    if (!tape_dm || !targets || !idx || !states || !scalars || !actions || !rewards) return TG_E_ARG;
+    if (((uintptr_t)tape_dm | (uintptr_t)targets) & 15) return TG_E_ARG;
+    if (replay_shift < 0 || replay_shift > 8) return TG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    // tokens are <= 8 (tape contract), so |coefficient| <= cmax; the 16-bit packed head is exact while
+    // target_bound + R * cmax^3 fits an int16 lane
+    const long long cmax = replay_shift > 8 - replay_shift ? replay_shift : 8 - replay_shift;
+    const bool pack16 = (long long)target_bound + (long long)R * cmax * cmax * cmax <= 32767;
+    TG_SWITCH_S(S, {
+        const int rc = tg::launch_demo_sample_dm<kS>(tape_dm, (const uint8_t *)targets, targets_i16 != 0, pack16, N, R, dim_t, replay_shift,
+                                                     (const long long *)idx, nb, states, scalars, (long long *)actions, rewards, st);
+        if (rc != TG_OK) return rc;
+    });
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_tape_to_demo_major(const uint8_t *tape, int64_t tape_step_stride, uint8_t *tape_dm, int64_t N, int R, int S, void *stream) {
+    if (!tg::supported_S(S) || N < 0 || R < 1) return TG_E_ARG;
+    if (N == 0) return TG_OK;
+    if (!tape || !tape_dm) return TG_E_ARG;
+    if (((uintptr_t)tape | (uintptr_t)tape_dm | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
+    const int tp16 = ((3 * S + 15) & ~15) / 16;
+    const long long total = N * R * tp16;
+    const long long blocks = (total + 255) / 256;
+    tg::tape_to_demo_major_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(tape), tape_step_stride / 16, reinterpret_cast<uint4 *>(tape_dm), N, R, tp16);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }

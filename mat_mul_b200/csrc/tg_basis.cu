@@ -62,11 +62,13 @@ __device__ __forceinline__ void mode_pass(const int32_t *__restrict__ in, int32_
 }
 
 
-// only_marked: visit every game, redo those the fast kernel marked with BASIS_REDO
-template <int S>
+// only_marked: visit every game, redo those the fast kernel marked with BASIS_REDO (they leave with TG_FLAG_PATH_EXACT).
+// OUT16: the result is written as an int16 slab (TG_FLAG_RANGE: an entry does not fit int16) instead of an int8 slab
+// (TG_FLAG_RANGE: an entry left [-64, 63]).
+template <int S, bool OUT16>
 __global__ void __launch_bounds__(BasisCfg<S>::NT)
     basis_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
-                 int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N, int only_marked) {
+                 void *__restrict__ slab_out_v, uint8_t *__restrict__ flags, long long N, int only_marked) {
     using C = BasisCfg<S>;
     using G = Geo<S>;
     constexpr int NT = C::NT;
@@ -114,34 +116,55 @@ __global__ void __launch_bounds__(BasisCfg<S>::NT)
     mode_pass<S, NT>(s_a, s_b, s_m + 2 * C::S2); // contract c with C -> Z[i][j][k]
     __syncthreads();
     uint32_t bad = 0;
-    uint32_t *dst = reinterpret_cast<uint32_t *>(slab_out + n * G::GP);
-    for (int w = tid; w < G::GP / 4; w += NT) {
-        const int i = w / G::WR, c = w % G::WR;
-        uint32_t word = 0;
-        if (i < S) {
+    if constexpr (OUT16) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<int16_t *>(slab_out_v) + n * G::GP);
+        for (int w = tid; w < G::GP / 2; w += NT) { // two int16 per word
+            const int i = (2 * w) / G::RP, x = (2 * w) % G::RP;
+            uint32_t word = 0;
+            if (i < S) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int jk = 4 * c + q;
-                if (jk < C::S2) {
-                    const int v = s_b[i * C::S2 + jk];
-                    if (v < -64 || v > 63) bad = TG_FLAG_RANGE;
-                    word |= ((uint32_t)v & 0xFFu) << (8 * q);
+                for (int q = 0; q < 2; q++) {
+                    const int jk = x + q;
+                    if (jk < C::S2) {
+                        const int v = s_b[i * C::S2 + jk];
+                        if (v < -32768 || v > 32767) bad = TG_FLAG_RANGE;
+                        word |= ((uint32_t)v & 0xFFFFu) << (16 * q);
+                    }
                 }
             }
+            dst[w] = word;
         }
-        dst[w] = word;
+    } else {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<int8_t *>(slab_out_v) + n * G::GP);
+        for (int w = tid; w < G::GP / 4; w += NT) {
+            const int i = w / G::WR, c = w % G::WR;
+            uint32_t word = 0;
+            if (i < S) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int jk = 4 * c + q;
+                    if (jk < C::S2) {
+                        const int v = s_b[i * C::S2 + jk];
+                        if (v < -64 || v > 63) bad = TG_FLAG_RANGE;
+                        word |= ((uint32_t)v & 0xFFu) << (8 * q);
+                    }
+                }
+            }
+            dst[w] = word;
+        }
     }
     if (bad) atomicOr(s_flag, bad);
     __syncthreads();
-    if (tid == 0 && flags) flags[n] = (uint8_t)*s_flag;
+    if (tid == 0 && flags) flags[n] = (uint8_t)(*s_flag | (only_marked ? TG_FLAG_PATH_EXACT : 0u));
     }
     }
 }
 
 // ------------------------------------------------------------------ fast path
-template <int S>
+template <int S, bool OUT16 = false>
 struct BasisFast {
     using G = Geo<S>;
+    static constexpr int EB = OUT16 ? 2 : 1;            // bytes per entry of the OUTPUT tile
     static constexpr int LPW = (S == 9) ? 3 : 2;        // entries per packed word
     static constexpr int LB = (S == 9) ? 10 : 16;       // bits per lane
     static constexpr int LMAX = (1 << (LB - 1)) - 1;    // every entry must stay in [-LMAX, LMAX]
@@ -160,9 +183,9 @@ struct BasisFast {
     static constexpr int YROW = S * WP + (S == 16 ? 8 : 0); // words between Y[a][.][.] and Y[a+1][.][.], padded so that
                                                         // lanes that differ in the first index hit different banks
     static constexpr int YB = S * YROW * 4;             // bytes of Y (Z is written over it in place)
-    static constexpr int OROW = G::RP + (S == 16 ? 16 : 0); // row pitch of the OUTPUT tile (same reason); a padded
-                                                        // tile leaves row by row
-    static constexpr int TILE_BYTES = (((S * OROW > G::GP ? S * OROW : G::GP) + (S == 9 ? 32 : (S == 4 ? 16 : 0))) + 15) & ~15;
+    static constexpr int OROW = G::RP + (S == 16 ? 16 : 0); // row pitch (entries) of the OUTPUT tile (same reason); a
+                                                        // padded tile leaves row by row
+    static constexpr int TILE_BYTES = ((EB * (S * OROW > G::GP ? S * OROW : G::GP) + (S == 9 ? 32 : (S == 4 ? 16 : 0))) + 15) & ~15;
     // per game, every part 16-byte aligned: tile, Y/Z, A and B as int32 [S][RW], C as packed bytes [S][4 words],
     // {max|Y|, normA, normB, flag}
     static constexpr int GAME_BYTES = TILE_BYTES + YB + 2 * S * RW * 4 + S * 16 + 16;
@@ -191,11 +214,12 @@ __device__ __forceinline__ void st_vec(int32_t *p, const int in[VEC]) {
     *reinterpret_cast<typename VecW<VEC>::T *>(p) = v;
 }
 
-template <int S>
-__global__ void __launch_bounds__(BasisFast<S>::NT)
+template <int S, bool OUT16>
+__global__ void __launch_bounds__(BasisFast<S, OUT16>::NT)
     basis_fast_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
-                      int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
-    using F = BasisFast<S>;
+                      void *__restrict__ slab_out_v, uint8_t *__restrict__ flags, long long N) {
+    using F = BasisFast<S, OUT16>;
+    uint8_t *slab_out = reinterpret_cast<uint8_t *>(slab_out_v);
     using G = Geo<S>;
     constexpr int W = F::W, LPW = F::LPW, LB = F::LB, KW4 = F::KW4, S2 = S * S, RW = F::RW, CB = F::CB, VEC = F::VEC,
                   WP = F::WP, BB = F::BB, YROW = F::YROW, OROW = F::OROW;
@@ -373,6 +397,16 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
                 // every lane in [HALF-64, HALF+63]  <=>  (lane - (HALF-64)) < 128 in every lane
                 over |= (u[c] - (HALF - 64u) * ONE) & ((LMASK & ~127u) * ONE);
             }
+            if constexpr (OUT16) {
+                // int16 out: the lanes ARE the results (exact under the guard, |entry| <= LMAX <= 32767)
+                int16_t *d16 = reinterpret_cast<int16_t *>(s_tile) + rr * OROW + j * S + h * CB * LPW;
+#pragma unroll
+                for (int c = 0; c < CB; c++)
+#pragma unroll
+                    for (int l = 0; l < LPW; l++)
+                        if (h * CB * LPW + c * LPW + l < S) d16[c * LPW + l] = (int16_t)((int)((u[c] >> (LB * l)) & LMASK) - (int)HALF);
+                continue;
+            }
             uint8_t *dst = s_tile + rr * OROW + j * S + h * CB * LPW;
             if constexpr (S == 9) {
 #pragma unroll
@@ -386,19 +420,30 @@ __global__ void __launch_bounds__(BasisFast<S>::NT)
                     *reinterpret_cast<uint32_t *>(dst + 2 * c) = __byte_perm(u[c], u[c + 1], 0x6420);
             }
         }
-        if (over) s_st[3] = TG_FLAG_RANGE;
+        if (over && !OUT16) s_st[3] = TG_FLAG_RANGE;
+        if constexpr (OUT16 && (G::RP != S2 || G::GP != S * G::RP)) {
+            // the int16 tile does not inherit zero padding from the input game: row and game padding written here
+            int16_t *t16 = reinterpret_cast<int16_t *>(s_tile);
+            if (h == 0) {
+#pragma unroll
+                for (int x = S2; x < G::RP; x++) t16[rr * OROW + x] = 0;
+                if (rr == 0)
+                    for (int x = S * G::RP; x < G::GP; x++) t16[x] = 0;
+            }
+        }
     }
     fence_proxy_async();
     __syncthreads();
+    constexpr int EB = F::EB;
     if constexpr (OROW == G::RP) {
         if (live && t == 0 && fast) {
-            bulk_s2g(slab_out + (g0 + gl) * G::GP, s_tile, (uint32_t)G::GP);
+            bulk_s2g(slab_out + (g0 + gl) * G::GP * EB, s_tile, (uint32_t)(G::GP * EB));
             bulk_commit();
             bulk_wait<0>();
         }
     } else { // padded output tile: one bulk store per row
         if (live && t < S && fast) {
-            bulk_s2g(slab_out + (g0 + gl) * G::GP + t * G::RP, s_tile + t * OROW, (uint32_t)G::RP);
+            bulk_s2g(slab_out + ((g0 + gl) * G::GP + t * G::RP) * EB, s_tile + t * OROW * EB, (uint32_t)(G::RP * EB));
             bulk_commit();
             bulk_wait<0>();
         }
@@ -660,54 +705,82 @@ __global__ void __launch_bounds__(64)
 
 } // namespace tg
 
-extern "C" {
-
-int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, int8_t *slab_out, uint8_t *flags, int64_t N,
-                       int S, void *stream) {
+// int8 slab in; int8 slab out (out16 == 0) or int16 slab out
+static int change_of_basis_impl(const int8_t *slab_in, const int8_t *mats, int per_game, void *slab_out, int out16, uint8_t *flags,
+                                int64_t N, int S, void *stream) {
     if (!tg::supported_S(S) || N < 0) return TG_E_ARG;
     if (N == 0) return TG_OK;
-    if (!slab_in || !mats || !slab_out || slab_in == slab_out) return TG_E_ARG;
+    if (!slab_in || !mats || !slab_out || (const void *)slab_in == (const void *)slab_out) return TG_E_ARG;
     if (((uintptr_t)slab_in | (uintptr_t)slab_out) & 15) return TG_E_ARG;
     if (N > 0x7FFFFFFFLL) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const long long ms = per_game ? 3LL * S * S : 0;
-    // fast packed kernel first; it marks the games whose intermediates do not fit its lanes and the exact kernel
-    // redoes exactly those.  Without a flags array there is nowhere to leave the mark: exact kernel for all.
+    // a fast kernel first (tensor cores for 9x9x9 and 16x16x16, packed integer lanes for 4x4x4); it marks the games whose
+    // intermediates its arithmetic cannot hold exactly and the exact int32 kernel redoes exactly those (TG_FLAG_PATH_EXACT).
+    // Without a flags array there is nowhere to leave the mark: exact kernel for all.
     const int exact_grid = (int)(N < 148 * 32 ? N : 148 * 32);
-#define TG_BASIS_CASE(SS)                                                                                              \
-    case SS: {                                                                                                         \
-        using F = tg::BasisFast<SS>;                                                                                   \
-        if (flags) {                                                                                                   \
-            auto fast = tg::basis_fast_kernel<SS>;                                                                     \
-            TG_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));           \
-            fast<<<(unsigned)((N + F::GPC - 1) / F::GPC), F::NT, F::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out, flags, N); \
-        }                                                                                                              \
-        tg::basis_kernel<SS><<<flags ? exact_grid : (int)N, tg::BasisCfg<SS>::NT, tg::BasisCfg<SS>::SMEM_BYTES, st>>>(  \
-            slab_in, mats, ms, slab_out, flags, N, flags ? 1 : 0);                                                     \
-    } break;
-    // S = 16: the tensor-core kernel (tg_basis_mma.cu) takes the place of the packed fast kernel; TG_BASIS_VARIANT=1
-    // keeps the packed kernel (A/B timing only)
+#define TG_BASIS_EXACT(SS, O16)                                                                                            \
+    tg::basis_kernel<SS, O16><<<flags ? exact_grid : (int)N, tg::BasisCfg<SS>::NT, tg::BasisCfg<SS>::SMEM_BYTES, st>>>(    \
+        slab_in, mats, ms, slab_out, flags, N, flags ? 1 : 0);
+#define TG_BASIS_FAST(SS, O16)                                                                                             \
+    {                                                                                                                      \
+        using F = tg::BasisFast<SS, O16>;                                                                                  \
+        auto fast = tg::basis_fast_kernel<SS, O16>;                                                                        \
+        TG_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));                   \
+        fast<<<(unsigned)((N + F::GPC - 1) / F::GPC), F::NT, F::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out, flags, N);  \
+    }
 #ifdef TG_TUNING
-    static const int variant = tg::tuning_env("TG_BASIS_VARIANT", 0);
+    static const int variant = tg::tuning_env("TG_BASIS_VARIANT", 0); // 1: packed integer lanes instead of the tensor cores
 #else
     constexpr int variant = 0;
 #endif
-    if (S == 16 && flags && variant != 1 && (((uintptr_t)mats | (uintptr_t)ms) & 3) == 0) {
-        const int rc = tg::launch_basis_mma16(slab_in, mats, ms, slab_out, flags, N, st);
-        if (rc != TG_OK) return rc;
-        tg::basis_kernel<16><<<exact_grid, tg::BasisCfg<16>::NT, tg::BasisCfg<16>::SMEM_BYTES, st>>>(slab_in, mats, ms, slab_out,
-                                                                                                 flags, N, 1);
-        TG_CUDA(cudaGetLastError());
-        return TG_OK;
-    }
+    const bool mats_ok = (((uintptr_t)mats | (uintptr_t)ms) & 3) == 0;
     switch (S) {
-        TG_BASIS_CASE(4)
-        TG_BASIS_CASE(9)
-        TG_BASIS_CASE(16)
+    case 4:
+        if (flags) {
+            if (out16) TG_BASIS_FAST(4, true) else TG_BASIS_FAST(4, false)
+        }
+        if (out16) { TG_BASIS_EXACT(4, true) } else { TG_BASIS_EXACT(4, false) }
+        break;
+    case 9:
+        if (flags && variant != 1) {
+            const int rc = tg::launch_basis_mma9(slab_in, mats, ms, slab_out, out16, flags, N, st);
+            if (rc != TG_OK) return rc;
+        } else if (flags) {
+            if (out16) TG_BASIS_FAST(9, true) else TG_BASIS_FAST(9, false)
+        }
+        if (out16) { TG_BASIS_EXACT(9, true) } else { TG_BASIS_EXACT(9, false) }
+        break;
+    case 16:
+        if (flags && variant != 1 && mats_ok) {
+            const int rc = tg::launch_basis_mma16(slab_in, mats, ms, slab_out, out16, flags, N, st);
+            if (rc != TG_OK) return rc;
+        } else if (flags) {
+#ifdef TG_TUNING
+            if (out16) TG_BASIS_FAST(16, true) else TG_BASIS_FAST(16, false)
+#else
+            cudaMemsetAsync(flags, tg::BASIS_REDO, (size_t)N, st); // unaligned matrices: every game through the exact kernel
+#endif
+        }
+        if (out16) { TG_BASIS_EXACT(16, true) } else { TG_BASIS_EXACT(16, false) }
+        break;
     }
-#undef TG_BASIS_CASE
+#undef TG_BASIS_EXACT
+#undef TG_BASIS_FAST
     TG_CUDA(cudaGetLastError());
     return TG_OK;
+}
+
+extern "C" {
+
+int tg_change_of_basis(const int8_t *slab_in, const int8_t *mats, int per_game, int8_t *slab_out, uint8_t *flags, int64_t N,
+                       int S, void *stream) {
+    return change_of_basis_impl(slab_in, mats, per_game, slab_out, 0, flags, N, S, stream);
+}
+
+int tg_change_of_basis_i16(const int8_t *slab_in, const int8_t *mats, int per_game, int16_t *slab16_out, uint8_t *flags, int64_t N,
+                           int S, void *stream) {
+    return change_of_basis_impl(slab_in, mats, per_game, slab16_out, 1, flags, N, S, stream);
 }
 
 int tg_change_of_basis_factors(const uint8_t *tape_in, int64_t in_step_stride, int shift_in, const int8_t *mats, int per_game,

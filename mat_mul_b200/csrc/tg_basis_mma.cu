@@ -134,6 +134,28 @@ __device__ __forceinline__ void finish4(const uint32_t (&d)[4][4], uint32_t &ove
     }
 }
 
+// int16 out: sixteen results d[k' & 3][x] -> eight int16 pairs.  F16: the accumulators started at 1.5 * 2^23 + 2^15, so the low
+// half of the bit pattern is the result in offset binary and the high half is 0x4B40 iff the result fits int16; P16: the low
+// half is the result modulo 2^16 (its guard already proved that it fits).
+template <bool F16>
+__device__ __forceinline__ void finish4_i16(const uint32_t (&d)[4][4], uint32_t &over, uint32_t (&outw)[4][8], int kq) {
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        const uint32_t w01 = prmt(d[0][x], d[1][x], 0x5410u), w23 = prmt(d[2][x], d[3][x], 0x5410u);
+        if constexpr (F16) {
+            over |= (prmt(d[0][x], d[1][x], 0x7632u) ^ 0x4B404B40u) | (prmt(d[2][x], d[3][x], 0x7632u) ^ 0x4B404B40u);
+            outw[x][2 * kq] = w01 ^ 0x80008000u, outw[x][2 * kq + 1] = w23 ^ 0x80008000u;
+        } else {
+            outw[x][2 * kq] = w01, outw[x][2 * kq + 1] = w23;
+        }
+    }
+}
+
+// |h| of both halves of an f16x2 word, folded into a running maximum (exactness check of the f16 operands)
+__device__ __forceinline__ void track_abs_max(__half2 &m, uint32_t w) {
+    m = __hmax2(m, __habs2(*reinterpret_cast<const __half2 *>(&w)));
+}
+
 // everything after the loads, for one game held by one warp.  fm: fragments of C (int8), of A and B with the columns
 // permuted to 2t, 2t+1, 8+2t, 9+2t (int8; the K-slot order of P16's pass 2 and the source of the f16 fragments) and of A
 // with its natural columns 4t..4t+3 (P16's pass 3).
@@ -141,11 +163,15 @@ struct Frags {
     uint32_t c0, c1, pa0, pa1, pb0, pb1, na0, na1;
 };
 
-template <bool F16, bool STREAM>
-__device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint32_t *__restrict__ src, const Frags &fm, int nA,
-                                                 int nB, int nC, uint32_t *sw, int8_t *__restrict__ out,
+// OUT16: int16 slab out.  CHECK (F16 only): the a-priori norm guard did not hold, so every f16 operand is checked as it is
+// produced (|Y|, |Z| <= 2047 keeps the f16 conversion exact, and then every f32 sum is exact too); returns false -- before
+// anything has been written -- if one is not, and the caller falls back to the byte-plane path.
+template <bool F16, bool STREAM, bool OUT16, bool CHECK>
+__device__ __forceinline__ bool basis_mma16_game(uint32_t (&tw)[32], const uint32_t *__restrict__ src, const Frags &fm, int nA,
+                                                 int nB, int nC, uint32_t *sw, void *__restrict__ out_v,
                                                  uint8_t *__restrict__ flag, int lane) {
     const int g = lane >> 2, t = lane & 3;
+    __half2 opmax = __float2half2_rn(0.f), zmax = __float2half2_rn(0.f); // CHECK: largest |Y| and |Z| operand of this lane
     uint32_t hA[4], hB[4]; // F16: the f16 fragments (rows g | g+8, k = 2t, 2t+1 | 2t+8, 2t+9)
     if constexpr (F16) {
         hA[0] = bytes_to_f16(fm.pa0, 0, 1), hA[1] = bytes_to_f16(fm.pa1, 0, 1);
@@ -177,6 +203,7 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
                 if constexpr (F16) {
                     const uint32_t b0 = pack_f16(__int_as_float(y0[2 * hk]) - MAGIC, __int_as_float(y0[2 * hk + 1]) - MAGIC);
                     const uint32_t b1 = pack_f16(__int_as_float(y1[2 * hk]) - MAGIC, __int_as_float(y1[2 * hk + 1]) - MAGIC);
+                    if constexpr (CHECK) track_abs_max(opmax, b0), track_abs_max(opmax, b1);
                     zf[aa][hk][0] = zf[aa][hk][1] = zf[aa][hk][2] = zf[aa][hk][3] = 0.f;
                     mma_f16(zf[aa][hk], hB, b0, b1);
                 } else {
@@ -198,6 +225,7 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
                     if constexpr (F16) { // slots a / 2 = 2q, 2q + 1
                         w0[2 * hk + ek] = pack_f16(zf[0][hk][x], zf[1][hk][x]);
                         w1[2 * hk + ek] = pack_f16(zf[2][hk][x], zf[3][hk][x]);
+                        if constexpr (CHECK) track_abs_max(zmax, w0[2 * hk + ek]), track_abs_max(zmax, w1[2 * hk + ek]);
                     } else { // slots q (low bytes), 4 + q (high bytes)
                         pack_planes(zi[0][hk][x], zi[1][hk][x], zi[2][hk][x], zi[3][hk][x], w0[2 * hk + ek], w1[2 * hk + ek]);
                     }
@@ -212,8 +240,16 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
         const long long ybound = 256LL * ((long long)warp_or_bytes(ymag) + 1);
         if (!(nC <= 255 && ybound * nA * nB <= 32767)) {
             if (lane == 0) *flag = BASIS_REDO;
-            return;
+            return true;
         }
+    }
+    if constexpr (F16 && CHECK) {
+        // 2047 is the largest integer below which every integer is an f16; a value that rounded is >= 2048 after rounding too
+        const float ym = fmaxf(__low2float(opmax), __high2float(opmax)), zm = fmaxf(__low2float(zmax), __high2float(zmax));
+        bool viol = !(ym <= 2047.f && zm <= 2047.f);
+        // int8 out: the range test below reads the low 16 bits of the results, so they must fit 16 bits: |T'| <= max|Z| ||A||
+        if constexpr (!OUT16) viol |= !(zm * (float)nA <= 32767.f);
+        if (__any_sync(0xFFFFFFFFu, viol)) return false;
     }
     __syncwarp();
 
@@ -229,7 +265,7 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
             r0[4 * s] = l4.x, r0[4 * s + 1] = l4.y, r0[4 * s + 2] = l4.z, r0[4 * s + 3] = l4.w;
             r1[4 * s] = h4.x, r1[4 * s + 1] = h4.y, r1[4 * s + 2] = h4.z, r1[4 * s + 3] = h4.w;
         }
-        uint32_t outw[4][4]; // [2 * (i' half) + (j' & 1)][k' / 4]
+        uint32_t outw[4][OUT16 ? 8 : 4]; // [2 * (i' half) + (j' & 1)][k' / 4 (int8) or k' / 2 (int16)]
 #pragma unroll
         for (int kq = 0; kq < 4; kq++) {
             uint32_t d[4][4]; // [k' & 3][2 * (i' half) + (j' & 1)]
@@ -237,7 +273,8 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
             for (int e = 0; e < 4; e++) {
                 const int kp = 4 * kq + e, idx = 4 * ((kp & 7) >> 1) + 2 * (kp >> 3) + (kp & 1);
                 if constexpr (F16) {
-                    float f[4] = {MAGIC, MAGIC, MAGIC, MAGIC};
+                    constexpr float M0 = OUT16 ? MAGIC + 32768.f : MAGIC;
+                    float f[4] = {M0, M0, M0, M0};
                     mma_f16(f, hA, r0[idx], r1[idx]);
 #pragma unroll
                     for (int x = 0; x < 4; x++) d[e][x] = __float_as_uint(f[x]);
@@ -248,25 +285,36 @@ __device__ __forceinline__ void basis_mma16_game(uint32_t (&tw)[32], const uint3
                     for (int x = 0; x < 4; x++) d[e][x] = (uint32_t)v[x];
                 }
             }
-            finish4(d, over, outw, kq);
+            if constexpr (OUT16)
+                finish4_i16<F16>(d, over, outw, kq);
+            else
+                finish4(d, over, outw, kq);
         }
 #pragma unroll
         for (int x = 0; x < 4; x++) {
             const int ip = g + 8 * (x >> 1), jp = 8 * hj + 2 * t + (x & 1);
-            *reinterpret_cast<uint4 *>(out + ip * 256 + jp * 16) = make_uint4(outw[x][0], outw[x][1], outw[x][2], outw[x][3]);
+            if constexpr (OUT16) {
+                uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(out_v) + ip * 256 + jp * 16);
+                o[0] = make_uint4(outw[x][0], outw[x][1], outw[x][2], outw[x][3]);
+                o[1] = make_uint4(outw[x][4], outw[x][5], outw[x][6], outw[x][7]);
+            } else {
+                *reinterpret_cast<uint4 *>(reinterpret_cast<int8_t *>(out_v) + ip * 256 + jp * 16) =
+                    make_uint4(outw[x][0], outw[x][1], outw[x][2], outw[x][3]);
+            }
         }
     }
     const bool bad = __any_sync(0xFFFFFFFFu, over != 0);
-    if (lane == 0) *flag = bad ? (uint8_t)TG_FLAG_RANGE : (uint8_t)0;
+    if (lane == 0) *flag = (uint8_t)((bad ? TG_FLAG_RANGE : 0u) | (F16 ? 0u : TG_FLAG_PATH_PLANES));
+    return true;
 }
 
 // MINB: CTAs per SM the register budget is sized for; STREAM: load the slab words four a at a time (one group ahead)
 // instead of all 32 up front; PATHS: 0 = F16 where its guard holds, else P16 (default), 1 = P16 only (tuning);
 // PREFETCH: L2 prefetch distance in CTAs per SM (0 = none)
-template <int MINB, bool STREAM, int PATHS, int PREFETCH>
+template <int MINB, bool STREAM, int PATHS, int PREFETCH, bool OUT16>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
     basis_mma16_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
-                       int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
+                       void *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
     extern __shared__ __align__(16) uint32_t s_words[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const long long n = (long long)blockIdx.x * WARPS + warp;
@@ -298,32 +346,34 @@ __global__ void __launch_bounds__(32 * WARPS, MINB)
     fm.pb0 = prmt(__ldg(mw + 64 + g * 4 + (t >> 1)), __ldg(mw + 64 + g * 4 + 2 + (t >> 1)), sel);
     fm.pb1 = prmt(__ldg(mw + 64 + (g + 8) * 4 + (t >> 1)), __ldg(mw + 64 + (g + 8) * 4 + 2 + (t >> 1)), sel);
     const int nA = norm_inf(fm.pa0, fm.pa1), nB = norm_inf(fm.pb0, fm.pb1), nC = norm_inf(fm.c0, fm.c1);
-    int8_t *out = slab_out + n * 4096;
+    void *out = reinterpret_cast<uint8_t *>(slab_out) + n * 4096 * (OUT16 ? 2 : 1);
     if constexpr (PATHS == 0) {
         // the a-priori bound needs max|T|: the whole game is read first
         uint32_t tm = 0;
 #pragma unroll
         for (int q = 0; q < 32; q++) tm |= mag4(tw[q]);
         const long long yb = ((long long)warp_or_bytes(tm) + 1) * nC, zb = yb * nB;
-        if (yb <= 2048 && zb <= 2048 && zb * nA <= 32767) {
-            basis_mma16_game<true, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
+        if (yb <= 2047 && zb <= 2047 && (OUT16 || zb * nA <= 32767)) { // every operand is an exact f16 whatever the game
+            basis_mma16_game<true, false, OUT16, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
             return;
         }
-        basis_mma16_game<false, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
+        // bigger matrices (SURVEY 8(d)'s density 0.3): the bound is far from tight, so try f16 and check the operands
+        if (basis_mma16_game<true, false, OUT16, true>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane)) return;
+        basis_mma16_game<false, false, OUT16, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
     } else {
-        basis_mma16_game<false, STREAM>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
+        basis_mma16_game<false, STREAM, OUT16, false>(tw, src, fm, nA, nB, nC, sw, out, flags + n, lane);
     }
 }
 
 } // namespace
 
-int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, int8_t *slab_out, uint8_t *flags,
+int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, void *slab_out, int out16, uint8_t *flags,
                        long long N, cudaStream_t st) {
     constexpr int SMEM = WARPS * WARP_WORDS * 4;
     const unsigned grid = (unsigned)((N + WARPS - 1) / WARPS);
 #define TG_MMA16_LAUNCH(MINB, STREAM, PATHS, PF)                                                                        \
     {                                                                                                                  \
-        auto kern = basis_mma16_kernel<MINB, STREAM, PATHS, PF>;                                                                \
+        auto kern = out16 ? basis_mma16_kernel<MINB, STREAM, PATHS, PF, true> : basis_mma16_kernel<MINB, STREAM, PATHS, PF, false>; \
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));                        \
         kern<<<grid, 32 * WARPS, SMEM, st>>>(slab_in, mats, mat_stride, slab_out, flags, N);                           \
     }

@@ -51,9 +51,12 @@ inline int cuda_fail(cudaError_t e) {
 
 // change of basis: set by a fast kernel on the games it leaves to the exact int32 kernel, which clears it
 constexpr uint8_t BASIS_REDO = 0x80;
-// tg_basis_mma.cu: 16x16x16 games, one warp per game on mma.sync int8
-int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, int8_t *slab_out, uint8_t *flags,
+// tg_basis_mma.cu: 16x16x16 games, one warp per game on mma.sync int8 + f16; tg_basis_mma9.cu: 9x9x9 games on mma.sync f16.
+// slab_out is an int8 slab (out16 == 0) or an int16 slab.
+int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_stride, void *slab_out, int out16, uint8_t *flags,
                        long long N, cudaStream_t st);
+int launch_basis_mma9(const int8_t *slab_in, const int8_t *mats, long long mat_stride, void *slab_out, int out16, uint8_t *flags,
+                      long long N, cudaStream_t st);
 
 // tg_demo_mma.cu: sum of the R rank-1 terms of 16x16x16 action lists, one warp per demo on mma.sync f16 (R <= 64)
 bool demo_acc16_mma_applies(int R);

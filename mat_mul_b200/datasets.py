@@ -63,11 +63,15 @@ class SyntheticDemoDataset(Dataset):
         if n_stored < n_demos:
             new_tape, new_slab = self._generate(n_demos - n_stored)
             tape = torch.cat((tape, new_tape), dim=1).contiguous()
+            if new_slab.dtype != slab.dtype:  # one int16 target makes the whole store int16
+                slab, new_slab = slab.to(torch.int16), new_slab.to(torch.int16)
             slab = torch.cat((slab, new_slab), dim=0).contiguous()
             torch.save({"tape": tape.cpu(), "slab": slab.cpu(), "max_actions": max_actions, "dim_3d": dim_3d,
                         "shift": shift}, store)
         # like the reference: more stored demos than asked for are simply not indexed (datasets.py:71-72)
         self._tape, self._slab = tape, slab
+        # what __getitem__ reads: demo-major action records + targets (int8 slab, or int16 where a target left its zone)
+        self._store = _env.DemoStore.from_tape(tape, slab, dim_3d, shift)
 
     # -- store ------------------------------------------------------------------------------------------
     def _load_existing(self, store: Path, tape, slab):
@@ -82,7 +86,9 @@ class SyntheticDemoDataset(Dataset):
             toks = torch.stack([torch.stack(torch.load(self.save_dir / f"action_seq_{i}.pt")) for i in range(n_ref)])
             tgts = torch.stack([torch.load(self.save_dir / f"target_tensor_{i}.pt") for i in range(n_ref)])
             tape = _env.pack_actions(toks.reshape(-1, 3 * S).to(self._cuda), S).reshape(n_ref, self.max_actions, -1)
-            return tape.transpose(0, 1).contiguous(), _env.pack_states(tgts.to(self._cuda).float().contiguous(), S)
+            tgts = tgts.to(self._cuda).float().contiguous()
+            wide = bool(tgts.abs().max() > 63) if n_ref else False
+            return tape.transpose(0, 1).contiguous(), (_env.pack_states16(tgts, S) if wide else _env.pack_states(tgts, S))
         return tape, slab
 
     def _generate(self, n: int):
@@ -90,7 +96,11 @@ class SyntheticDemoDataset(Dataset):
         tape, slab, flags, _ = _env.demos_from_seed(n, self.max_actions, self.dim_3d, self.values.tolist(),
                                                     self.probs.tolist(), self.shift, seed=None, device=self._cuda)
         if bool((flags & _env.FLAG_RANGE).any()):
-            raise TensorGameError("a synthetic target left the int8 slab's guaranteed range [-64, 63]")
+            # a target left the int8 slab's zone (the reference accumulates in float32 without limit, utils.py:218-232):
+            # the same action lists summed into the int16 format
+            slab, f16 = _env.accumulate_demos16(tape, self.dim_3d, self.shift)
+            if bool((f16 & _env.FLAG_RANGE).any()):
+                raise TensorGameError("a synthetic target does not fit int16")
         return tape, slab
 
     # -- Dataset ----------------------------------------------------------------------------------------
@@ -105,7 +115,7 @@ class SyntheticDemoDataset(Dataset):
         if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_items):
             raise IndexError(f"sample index out of range [0, {n_items})")
         # the reference replays with action_to_tensor, whose shift is fixed at 1
-        out = _env.demo_samples(self._tape, self._slab, idx, self.dim_3d, self.dim_t, replay_shift=1)
+        out = self._store.samples(idx, self.dim_t, replay_shift=1)
         return tuple(t.to(self.device) for t in out)
 
     @torch.no_grad()
@@ -128,7 +138,7 @@ class SyntheticDemoDataset(Dataset):
         tape, slab = self._generate(n_demos_needed)
         S = self.dim_3d
         tokens = _env.unpack_actions(tape.reshape(-1, tape.shape[-1]), S).reshape(self.max_actions, n_demos_needed, 3 * S).cpu()
-        targets = _env.expand_states(slab, S).cpu()
+        targets = (_env.expand_states16(slab, S) if slab.dtype == torch.int16 else _env.expand_states(slab, S)).cpu()
         for d in range(n_demos_needed):
             yield [tokens[r, d] for r in range(self.max_actions)], targets[d]
 
@@ -155,8 +165,11 @@ class SyntheticDemoDataset(Dataset):
 
 
 class PlayedGamesDataset(Dataset):
-    """datasets.py:161-230: ring buffer of played games (states, policies, rewards per step); kept in host
-    memory instead of three .pt files per game."""
+    """datasets.py:161-230: ring buffer of played games (state, improved policy, reward per step).  The reference keeps
+    three .pt files per game on disk; here the ring lives in HBM: states as int16 slabs (buffer_size, L, T, GP), policies
+    float32 (buffer_size, L, n_steps, n_logits), rewards int64 (buffer_size, L), with L = the longest game seen (grown on
+    demand).  Same ring semantics: game_pointer wraps at buffer_size and a new game overwrites the slot it lands on;
+    items are indexed game by game in slot order."""
 
     def __init__(self, buffer_size: int, device: str, save_dir=SAVE_DIR_PLAYED_GAMES, **kwargs):
         super().__init__()
@@ -166,34 +179,75 @@ class PlayedGamesDataset(Dataset):
         self.device = device
         self.save_dir = Path(save_dir)
         self.save_dir.mkdir(parents=True, exist_ok=True)
-        self._games = {}
+        self._states = self._policy = self._reward = None
+        self._dims = None  # (T, S)
 
     def __del__(self):
-        self._games = {}
+        self._states = self._policy = self._reward = None
         self.game_pointer = 0
 
     def __len__(self):
         return sum(self.game_lengths.values())
 
-    @torch.no_grad()
-    def __getitem__(self, idx: int):
+    def _ensure(self, L: int, T: int, S: int, pol_shape):
+        dev = _device()
+        if self._states is None:
+            lay = _env.layout(S)
+            self._dims = (T, S)
+            self._states = torch.zeros((self.buffer_size, L, T, lay.game_pitch), dtype=torch.int16, device=dev)
+            self._policy = torch.zeros((self.buffer_size, L, *pol_shape), dtype=torch.float32, device=dev)
+            self._reward = torch.zeros((self.buffer_size, L), dtype=torch.int64, device=dev)
+        elif L > self._states.shape[1]:
+            grow = lambda x: torch.cat((x, x.new_zeros((x.shape[0], L - x.shape[1], *x.shape[2:]))), dim=1)  # noqa: E731
+            self._states, self._policy, self._reward = grow(self._states), grow(self._policy), grow(self._reward)
+        if self._dims != (T, S) or tuple(self._policy.shape[2:]) != tuple(pol_shape):
+            raise TensorGameError("PlayedGamesDataset: every game must have the same state and policy shape")
+
+    def add_game(self, state_seq: List[torch.Tensor], action_seq: List[torch.Tensor], reward_seq: List[torch.Tensor]):
+        n = len(state_seq)
+        states = torch.stack([s.reshape(s.shape[-4:]) for s in state_seq]).to(torch.float32)  # (n, T, S, S, S)
+        T, S = states.shape[1], states.shape[-1]
+        policy = torch.stack([torch.as_tensor(a) for a in action_seq]).to(torch.float32) if not isinstance(action_seq, torch.Tensor) else action_seq.to(torch.float32)
+        reward = torch.stack([torch.as_tensor(r).reshape(()) for r in reward_seq]) if not isinstance(reward_seq, torch.Tensor) else reward_seq
+        self._ensure(n, T, S, policy.shape[1:])
+        dev = self._states.device
+        slab16 = _env.pack_states16(states.reshape(n * T, S, S, S).to(dev).contiguous(), S)
+        g = self.game_pointer
+        self._states[g, :n] = slab16.reshape(n, T, -1)
+        self._policy[g, :n] = policy.to(dev)
+        self._reward[g, :n] = reward.to(dev).to(torch.int64)
+        self.game_lengths[g] = n
+        self.game_pointer = (self.game_pointer + 1) % self.buffer_size
+
+    def _locate(self, idx: int):
         i = 0
         while idx >= self.game_lengths[i]:
             idx -= self.game_lengths[i]
             i += 1
-        state_seq, action_seq, reward_seq = self._games[i]
-        return (
-            state_seq[idx].to(self.device),
-            get_scalars(state_seq[idx], idx, batch_size=False).to(self.device),
-            action_seq[idx].to(self.device).argmax(dim=-1),
-            reward_seq[idx].reshape(1).to(self.device),
-        )
+        return i, idx
 
-    def add_game(self, state_seq: List[torch.Tensor], action_seq: List[torch.Tensor], reward_seq: List[torch.Tensor]):
-        self.game_lengths[self.game_pointer] = len(state_seq)
-        # snapshot (the reference wrote the sequences to disk): later mutation by the caller must not change the buffer
-        self._games[self.game_pointer] = (list(state_seq), list(action_seq), list(reward_seq))
-        self.game_pointer = (self.game_pointer + 1) % self.buffer_size
+    def get_batch(self, indices):
+        """Collated items for many indices: one gather from the ring and one slab16 -> float32 expansion."""
+        T, S = self._dims
+        where = [self._locate(int(i)) for i in indices]
+        dev = self._states.device
+        g = torch.tensor([w[0] for w in where], dtype=torch.int64, device=dev)
+        j = torch.tensor([w[1] for w in where], dtype=torch.int64, device=dev)
+        slab16 = self._states[g, j].reshape(len(where) * T, -1).contiguous()
+        states = _env.expand_states16(slab16, S).reshape(len(where), T, S, S, S)
+        scalars = j.to(torch.float32).unsqueeze(1)                # get_scalars(state, idx, batch_size=False): the step index
+        actions = self._policy[g, j].argmax(dim=-1)
+        rewards = self._reward[g, j].unsqueeze(1)
+        return tuple(t.to(self.device) for t in (states, scalars, actions, rewards))
+
+    @torch.no_grad()
+    def __getitem__(self, idx: int):
+        st, sc, ac, rw = self.get_batch([idx])
+        return st[0], sc[0], ac[0], rw[0]
+
+    def __getitems__(self, indices):
+        st, sc, ac, rw = self.get_batch(list(indices))
+        return [(st[i], sc[i], ac[i], rw[i]) for i in range(len(indices))]
 
 
 class TensorGameDataset(Dataset):
@@ -250,9 +304,11 @@ class TensorGameDataset(Dataset):
             items = self.buffer_synth.__getitems__([routed[p][1] for p in synth_pos])
             for p, item in zip(synth_pos, items):
                 out[p] = item
-        for p, (buf, j) in enumerate(routed):
-            if out[p] is None:
-                out[p] = buf[j]
+        for other in (self.buffer_played, self.buffer_best):
+            pos = [p for p, (buf, _) in enumerate(routed) if buf is other]
+            if pos:
+                for p, item in zip(pos, other.__getitems__([routed[p][1] for p in pos])):
+                    out[p] = item
         return out
 
     def set_fractions(self, fract_synth, fract_best):

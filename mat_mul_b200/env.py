@@ -14,7 +14,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import FLAG_EXHAUSTED, FLAG_NULL, FLAG_RANGE, FLAG_TERMINAL, FLAG_TOKEN_RANGE, TensorGameError, check  # noqa: F401
+from ._lib import (FLAG_EXHAUSTED, FLAG_NULL, FLAG_PATH_EXACT, FLAG_PATH_PLANES, FLAG_RANGE, FLAG_TERMINAL,  # noqa: F401
+                   FLAG_TOKEN_RANGE, TensorGameError, check)
 
 
 @dataclass(frozen=True)
@@ -54,6 +55,11 @@ def _on(*tensors):
             raise TensorGameError(f"operands live on different devices ({dev} and {d})")
     with torch.cuda.device(dev):
         yield C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _stream() -> C.c_void_p:
+    """torch's current stream on the CURRENT device (for callers that drive the C ABI directly, e.g. the tests)."""
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _call(name: str, operands: tuple, *args) -> None:
@@ -114,6 +120,41 @@ def expand_states(slab: torch.Tensor, S: int, out: torch.Tensor | None = None) -
         out = torch.empty((B, S, S, S), dtype=torch.float32, device=slab.device)
     stride = out.stride(0) if B > 1 else S ** 3
     _call("tg_expand_f32", (slab, out,), _p(slab), _p(out), stride, B, S)
+    return out
+
+
+def slab16_view(slab16: torch.Tensor, S: int) -> torch.Tensor:
+    """Strided (B, S, S, S) int16 view of an int16 slab (no copy)."""
+    lay = layout(S)
+    return slab16.as_strided((slab16.shape[0], S, S, S), (lay.game_pitch, lay.row_pitch, S, 1))
+
+
+def pack_states16(heads: torch.Tensor, S: int | None = None) -> torch.Tensor:
+    """float32 heads (B, S, S, S) -> int16 slab (B, GP) of int16 (tg_pack_f32_i16): the format for residuals the int8
+    slab cannot hold.  Raises if a value is not an integer in [-32768, 32767]."""
+    if heads.dtype != torch.float32 or not heads.is_cuda:
+        raise TensorGameError("heads must be a CUDA float32 tensor")
+    S = S or heads.shape[-1]
+    B = heads.shape[0]
+    if heads.shape[1:] != (S, S, S) or heads[0].numel() and not heads[0].is_contiguous():
+        raise TensorGameError("heads must be (B, S, S, S) with dense games")
+    out = torch.empty((B, layout(S).game_pitch), dtype=torch.int16, device=heads.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=heads.device)
+    stride = heads.stride(0) if B > 1 else S ** 3
+    _call("tg_pack_f32_i16", (heads, out, flag), _p(heads), stride, _p(out), B, S, _p(flag))
+    if int(flag.item()):
+        raise TensorGameError("pack_states16: residual entries must be integers in [-32768, 32767]")
+    return out
+
+
+def expand_states16(slab16: torch.Tensor, S: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """int16 slab -> float32 (B, S, S, S) (tg_expand_f32_i16)."""
+    _need_cuda(slab16, "slab16", torch.int16)
+    B = slab16.shape[0]
+    if out is None:
+        out = torch.empty((B, S, S, S), dtype=torch.float32, device=slab16.device)
+    stride = out.stride(0) if B > 1 else S ** 3
+    _call("tg_expand_f32_i16", (slab16, out), _p(slab16), _p(out), stride, B, S)
     return out
 
 
@@ -271,6 +312,23 @@ def accumulate_demos(tape: torch.Tensor, S: int, shift: int, slab: torch.Tensor 
     return slab, flags
 
 
+def accumulate_demos16(tape: torch.Tensor, S: int, shift: int, slab16: torch.Tensor | None = None):
+    """The same sum as accumulate_demos into an int16 slab (tg_demo_accumulate_i16): exact for every tape; the flag
+    says an entry does not fit int16.  Where targets beyond the int8 slab's zone go (the reference accumulates them in
+    float32 without limit, utils.py:218-232).  Returns (slab16 int16 (N, GP), flags)."""
+    _need_cuda(tape, "tape", torch.uint8)
+    lay = layout(S)
+    R, N = tape.shape[0], tape.shape[1]
+    if tape.shape[2] != lay.token_pitch:
+        raise TensorGameError(f"tape must be (R, N, {lay.token_pitch})")
+    if slab16 is None:
+        slab16 = torch.empty((N, lay.game_pitch), dtype=torch.int16, device=tape.device)
+    flags = torch.empty(N, dtype=torch.uint8, device=tape.device)
+    stride = tape.stride(0) if R > 1 else N * lay.token_pitch
+    _call("tg_demo_accumulate_i16", (tape, slab16, flags), _p(tape), stride, N, R, S, shift, _p(slab16), _p(flags))
+    return slab16, flags
+
+
 def torch_cpu_stream(n: int, seed: int | None = None, generator: torch.Generator | None = None, skip: int = 0):
     """The next n doubles torch's CPU generator would produce (torch.rand(dtype=float64)), computed by the
     library's MT19937 (tg_mt19937_fill_f64*) WITHOUT advancing torch's generator.  seed=None continues from
@@ -378,12 +436,74 @@ def demo_samples(tape: torch.Tensor, slab: torch.Tensor, idx: torch.Tensor, S: i
     return states, scalars, actions, rewards
 
 
+class DemoStore:
+    """The in-HBM demonstration store the training-sample batcher reads (replaces the two .pt files per demo of
+    datasets.py:62-69): demo-major action records uint8 (N, R, TP) -- the records a .. R-1 one sample needs are one
+    contiguous run -- and the targets as an int8 slab, or an int16 slab when a target left the int8 zone."""
+
+    def __init__(self, records: torch.Tensor, targets: torch.Tensor, S: int, shift: int, target_bound: int | None = None):
+        _need_cuda(records, "records", torch.uint8)
+        lay = layout(S)
+        if records.dim() != 3 or records.shape[2] != lay.token_pitch:
+            raise TensorGameError(f"records must be (N, R, {lay.token_pitch})")
+        if targets.dtype not in (torch.int8, torch.int16) or targets.shape != (records.shape[0], lay.game_pitch) or not targets.is_cuda:
+            raise TensorGameError(f"targets must be an int8 or int16 slab (N, {lay.game_pitch})")
+        self.records, self.targets, self.S, self.shift = records, targets.contiguous(), S, shift
+        self.N, self.R = records.shape[0], records.shape[1]
+        if target_bound is None:
+            target_bound = 127 if targets.dtype == torch.int8 else (int(targets.abs().max()) if self.N else 0)
+        self.target_bound = int(target_bound)
+
+    @classmethod
+    def from_tape(cls, tape: torch.Tensor, targets: torch.Tensor, S: int, shift: int) -> "DemoStore":
+        """From a step-major tape (R, N, TP) (tg_tape_to_demo_major) and its target slab."""
+        _need_cuda(tape, "tape", torch.uint8)
+        R, N = tape.shape[0], tape.shape[1]
+        records = torch.empty((N, R, tape.shape[2]), dtype=torch.uint8, device=tape.device)
+        stride = tape.stride(0) if R > 1 else N * tape.shape[2]
+        _call("tg_tape_to_demo_major", (tape, records), _p(tape), stride, _p(records), N, R, S)
+        return cls(records, targets, S, shift)
+
+    def tape(self) -> torch.Tensor:
+        """The step-major view (R, N, TP) of the records (a strided view, no copy)."""
+        return self.records.transpose(0, 1)
+
+    def samples(self, idx: torch.Tensor, dim_t: int, replay_shift: int = 1):
+        """Batch of SyntheticDemoDataset.__getitem__ results (datasets.py:77-122) for sample indices demo * R + action
+        (tg_demo_sample_dm).  Returns (states f32 (nb,dim_t,S,S,S), scalars f32 (nb,1), actions i64 (nb,3S), rewards f32 (nb,1))."""
+        _need_cuda(idx, "idx", torch.int64)
+        S, nb, dev = self.S, idx.numel(), self.records.device
+        states = torch.empty((nb, dim_t, S, S, S), dtype=torch.float32, device=dev)
+        scalars = torch.empty((nb, 1), dtype=torch.float32, device=dev)
+        actions = torch.empty((nb, 3 * S), dtype=torch.int64, device=dev)
+        rewards = torch.empty((nb, 1), dtype=torch.float32, device=dev)
+        _call("tg_demo_sample_dm", (self.records, self.targets, idx, states, scalars, actions, rewards), _p(self.records),
+              _p(self.targets), int(self.targets.dtype == torch.int16), self.target_bound, self.N, self.R, S, dim_t, replay_shift,
+              _p(idx), nb, _p(states), _p(scalars), _p(actions), _p(rewards))
+        return states, scalars, actions, rewards
+
+
 def slice_rank(slab: torch.Tensor, S: int) -> torch.Tensor:
     """get_rank per game (utils.py:134-140): int32 (B,)."""
     _need_cuda(slab, "slab", torch.int8)
     ranks = torch.empty(slab.shape[0], dtype=torch.int32, device=slab.device)
     _call("tg_slice_rank", (slab, ranks,), _p(slab), _p(ranks), slab.shape[0], S)
     return ranks
+
+
+def episode_returns(final_slab: torch.Tensor, steps: torch.Tensor, S: int, max_len: int | None = None):
+    """The played-game return rule of actor_prediction (act.py:59-62) for a batch of finished games:
+    reward_seq = cumsum([-1] * (n - 1) + [-1 - get_rank(final state)]) with n = steps[b] actions played, i.e.
+    -1, -2, ..., -(n-1), -n - rank; the rank is tg_slice_rank of the final head (0 for a solved game).
+    Returns (returns int64 (B,) = reward_seq[n-1], reward_seq int64 (B, K) zero-padded beyond n, ranks int32 (B,))."""
+    ranks = slice_rank(final_slab, S)
+    n = steps.to(torch.int64)
+    r = ranks.to(torch.int64)
+    K = int(max_len if max_len is not None else (int(n.max()) if n.numel() else 0))
+    t = torch.arange(1, K + 1, device=n.device, dtype=torch.int64).unsqueeze(0)
+    seq = torch.where(t == n.unsqueeze(1), -t - r.unsqueeze(1), -t)
+    seq = torch.where(t <= n.unsqueeze(1), seq, torch.zeros_like(seq))
+    return -n - r, seq, ranks
 
 
 def state_keys(slab: torch.Tensor, S: int) -> torch.Tensor:
@@ -407,11 +527,14 @@ def sample_unimodular(n: int, S: int, seed: int = 0, first: int = 0, p_nonzero: 
 
 
 def change_of_basis(slab: torch.Tensor, mats: torch.Tensor, S: int, tape: torch.Tensor | None = None, shift: int = 0,
-                    shift_out: int | None = None):
+                    shift_out: int | None = None, out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.int8,
+                    return_path_stats: bool = False):
     """T' = T x1 A x2 B x3 C (and u' = A u, v' = B v, w' = C w for a step-major tape).
 
-    mats int8 (N, 3, S, S) per game or (1, 3, S, S) / (3, S, S) shared.  Returns (slab', flags) or
-    (slab', tape', flags).  Not in the reference: AlphaTensor paper, Methods "Change of basis"."""
+    mats int8 (N, 3, S, S) per game or (1, 3, S, S) / (3, S, S) shared.  The result is an int8 slab (flag RANGE: an
+    entry left [-64, 63]) or, with out_dtype / out of torch.int16, an int16 slab (SURVEY 8(d)'s format; flag RANGE: an
+    entry does not fit int16).  Returns (slab', flags) or (slab', tape', flags); with return_path_stats a dict counting
+    the games per kernel path is appended.  Not in the reference: AlphaTensor paper, Methods "Change of basis"."""
     _need_cuda(slab, "slab", torch.int8)
     _need_cuda(mats, "mats", torch.int8)
     N = slab.shape[0]
@@ -419,19 +542,28 @@ def change_of_basis(slab: torch.Tensor, mats: torch.Tensor, S: int, tape: torch.
     if m.shape[0] not in (1, N):
         raise TensorGameError("mats must hold one (A,B,C) triple or one per game")
     per_game = int(m.shape[0] == N and N > 1)
-    out = torch.empty_like(slab)
+    if out is None:
+        out = torch.empty(slab.shape, dtype=out_dtype, device=slab.device)
+    if out.dtype not in (torch.int8, torch.int16) or out.shape != slab.shape or not out.is_contiguous():
+        raise TensorGameError("out must be a contiguous int8 or int16 slab of the input's shape")
     flags = torch.zeros(N, dtype=torch.uint8, device=slab.device)
-    _call("tg_change_of_basis", (slab, m, out, flags,), _p(slab), _p(m), per_game, _p(out), _p(flags), N, S)
+    name = "tg_change_of_basis_i16" if out.dtype == torch.int16 else "tg_change_of_basis"
+    _call(name, (slab, m, out, flags), _p(slab), _p(m), per_game, _p(out), _p(flags), N, S)
+    stats = None
+    if return_path_stats:
+        exact = int(((flags & FLAG_PATH_EXACT) != 0).sum().item())
+        planes = int(((flags & FLAG_PATH_PLANES) != 0).sum().item())
+        stats = {"games": N, "fast_path": N - exact - planes, "byte_plane_path": planes, "exact_int32_redo": exact}
     if tape is None:
-        return out, flags
+        return (out, flags, stats) if return_path_stats else (out, flags)
     _need_cuda(tape, "tape", torch.uint8)
     lay = layout(S)
     R = tape.shape[0]
     shift_out = shift if shift_out is None else shift_out
     tape_out = torch.empty_like(tape)
-    _call("tg_change_of_basis_factors", (tape, m, tape_out, flags,), _p(tape), N * lay.token_pitch, shift, _p(m), per_game, _p(tape_out),
-                                                N * lay.token_pitch, shift_out, _p(flags), N, R, S)
-    return out, tape_out, flags
+    _call("tg_change_of_basis_factors", (tape, m, tape_out, flags), _p(tape), N * lay.token_pitch, shift, _p(m), per_game,
+          _p(tape_out), N * lay.token_pitch, shift_out, _p(flags), N, R, S)
+    return (out, tape_out, flags, stats) if return_path_stats else (out, tape_out, flags)
 
 
 def bind_host_to_gpu(device: int = 0) -> list[int]:

@@ -223,7 +223,8 @@ def test_change_of_basis_tensor_core_path_16(env):
     f = flags.cpu().numpy()
     assert not (f & 0x80).any()
     assert np.array_equal((f & 4) != 0, ((want < -64) | (want > 63)).reshape(N, -1).any(1))
-    assert np.array_equal(f & ~np.uint8(4), np.zeros(N, dtype=np.uint8))
+    assert np.array_equal(f & ~np.uint8(4 | 32 | 64), np.zeros(N, dtype=np.uint8))  # besides RANGE only the informational path bits
+    assert (f & 64).any() and (f[::6] & (32 | 64) == 0).all()  # some games need the exact kernel; identities stay on the f16 path
     assert np.array_equal(slab_to_dense(out.cpu().numpy(), S).astype(np.int8), want.astype(np.int8))
     # one shared triple for every game
     out1, f1 = env.change_of_basis(slab, torch.from_numpy(m[2].astype(np.int8)).cuda(), S)
