@@ -468,6 +468,237 @@ __global__ void __launch_bounds__(SampleCfg<S>::NT)
     }
 }
 
+// ------------------------------------------------------------------ K4r: 9x9x9, one thread per (sample, row i)
+// The word-column kernel above spends ~1270 warp-instructions per 9x9x9 sample: every one of a sample's 21 threads
+// extracts all nine u coefficients of every replayed action and walks all of them.  Here a thread owns ROW i of its sample
+// (81 entries as 45 packed pairs of 16-bit lanes): per replayed action it needs ONE u coefficient -- and skips the action
+// altogether when that coefficient is zero (70 % of them with the reference's distributions; every lane walks its own list
+// of non-zero actions) -- forms c_j = u_i v_j once and adds c_j * pack(w) to its nine runs: 45 IMADs for 81 entries.  A WARP
+// is self-contained (three samples, no CTA barrier): it converts the later records of its samples into replay form (w as
+// five 16-bit pairs, u and v as int8 coefficients) in shared memory, and builds one state slot at a time in a warp-private
+// tile that is the image of the slot's 729 floats in HBM -- placed at the same offset modulo 16 bytes, so the aligned body
+// leaves with one TMA bulk store per (sample, slot) and at most three floats at either end with plain stores.  A row of 81
+// floats is 81 consecutive words of the tile and lanes are 81 words apart: conflict-free for the lanes of one sample.
+namespace rows9 {
+constexpr int S = 9, S2 = 81, S3 = 729, TP = 32, RP = 84, GP = 768;
+constexpr int WARPS = 3, SPW = 3;            // warps per CTA; samples per warp (27 of 32 lanes own a row)
+constexpr int RECB = 48;                     // replay record: 5 words pack16(w) | 5 words coefficient bytes (u 0..8, v 9..17) | pad
+constexpr int PIECE = 736;                   // floats per sample in the warp tile (729 + alignment phase, multiple of 4 and of 32)
+__host__ __device__ constexpr int warp_bytes(int R) { return ((SPW * R * RECB + 15) & ~15) + SPW * PIECE * 4; }
+
+template <int B>
+__device__ __forceinline__ int sx(uint32_t w) { return sext_byte<B>(w); }
+
+template <bool TGT16, bool PACK16>
+__global__ void __launch_bounds__(32 * WARPS, 6)
+    demo_sample_rows9_kernel(const uint8_t *__restrict__ tape_dm, const uint8_t *__restrict__ targets, long long N, int R, int dim_t,
+                             int replay_shift, const long long *__restrict__ idx, long long nb, float *__restrict__ states,
+                             float *__restrict__ scalars, long long *__restrict__ actions, float *__restrict__ rewards) {
+    static_assert(PACK16, "the row kernel keeps 16-bit lanes; the host routes larger bounds to the column kernel");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *s_rec = smem + (size_t)warp * warp_bytes(R);
+    float *s_tile = reinterpret_cast<float *>(s_rec + ((SPW * R * RECB + 15) & ~15));
+    const long long b0 = ((long long)blockIdx.x * WARPS + warp) * SPW;
+    if (b0 >= nb) return;
+    const int ns = (int)min((long long)SPW, nb - b0);
+    // ---- the warp's samples: lane q < ns reads index q; everybody gets (demo, a) of every sample by shuffle
+    long long my_demo = -1;
+    int my_a = -1;
+    if (lane < ns) {
+        const long long id = idx[b0 + lane];
+        if (id >= 0) {
+            split_index(id, R, my_demo, my_a);
+            if (my_demo >= N) my_demo = -1, my_a = -1;
+        }
+    }
+    long long demo_q[SPW];
+    int a_q[SPW];
+#pragma unroll
+    for (int q = 0; q < SPW; q++) {
+        demo_q[q] = __shfl_sync(0xFFFFFFFFu, my_demo, q);
+        a_q[q] = __shfl_sync(0xFFFFFFFFu, my_a, q);
+    }
+    const int q = lane / S, i = lane - q * S; // this lane's sample and row (lanes 27..31: q == 3, helpers only)
+    const bool owner = q < ns;
+    long long demo = -1;
+    int a = -1;
+#pragma unroll
+    for (int x = 0; x < SPW; x++)
+        if (x == q) demo = demo_q[x], a = a_q[x];
+    const bool live = owner && a >= 0;
+    // ---- this lane's target row in flight: 84 bytes (int8) / 162 bytes (int16) at a 4-byte aligned address; and its three
+    // tokens of the sample's own action (raw tokens: the actions output)
+    constexpr int TW = TGT16 ? 41 : 21;
+    uint32_t tw[TW];
+    uint32_t own[3] = {0, 0, 0};
+    if (live) {
+        const uint8_t *ta = tape_dm + ((size_t)demo * R + a) * TP;
+#pragma unroll
+        for (int x = 0; x < 3; x++) own[x] = __ldg(ta + i * 3 + x);
+        const uint32_t *tp = reinterpret_cast<const uint32_t *>(targets + ((size_t)demo * GP + i * RP) * (TGT16 ? 2 : 1));
+#pragma unroll
+        for (int w = 0; w < TW; w++) tw[w] = __ldg(tp + w);
+    }
+    // ---- the records j > a of the three samples -> replay form in shared memory, one record per lane and round
+    {
+        const uint32_t sh4 = (uint32_t)replay_shift * ONES4;
+        int n0 = a_q[0] >= 0 ? R - 1 - a_q[0] : 0, n1 = a_q[1] >= 0 ? R - 1 - a_q[1] : 0, n2 = a_q[2] >= 0 ? R - 1 - a_q[2] : 0;
+        for (int e = lane; e < n0 + n1 + n2; e += 32) {
+            const int x = (e >= n0) + (e >= n0 + n1);
+            const int j = (x == 0 ? a_q[0] + 1 + e : (x == 1 ? a_q[1] + 1 + e - n0 : a_q[2] + 1 + e - n0 - n1));
+            const long long d = x == 0 ? demo_q[0] : (x == 1 ? demo_q[1] : demo_q[2]);
+            const uint4 *src = reinterpret_cast<const uint4 *>(tape_dm + ((size_t)d * R + j) * TP);
+            const uint4 r0 = __ldg(src), r1 = __ldg(src + 1);
+            const uint32_t c0 = ((r0.x | H4) - sh4) ^ H4, c1 = ((r0.y | H4) - sh4) ^ H4, c2 = ((r0.z | H4) - sh4) ^ H4,
+                           c3 = ((r0.w | H4) - sh4) ^ H4, c4 = ((r1.x | H4) - sh4) ^ H4, c5 = ((r1.y | H4) - sh4) ^ H4,
+                           c6 = ((r1.z | H4) - sh4) ^ H4;
+            // w coefficients are bytes 18..26: c4.2, c4.3, c5.0..3, c6.0..2
+            const int p0 = sx<2>(c4) + sx<3>(c4) * 65536, p1 = sx<0>(c5) + sx<1>(c5) * 65536, p2 = sx<2>(c5) + sx<3>(c5) * 65536,
+                      p3 = sx<0>(c6) + sx<1>(c6) * 65536, p4 = sx<2>(c6);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_rec + ((size_t)x * R + j) * RECB);
+            dst[0] = make_uint4((uint32_t)p0, (uint32_t)p1, (uint32_t)p2, (uint32_t)p3);
+            dst[1] = make_uint4((uint32_t)p4, c0, c1, c2);
+            dst[2] = make_uint4(c3, c4, 0u, 0u);
+        }
+    }
+    __syncwarp();
+    const uint8_t *rbase = s_rec + (size_t)(owner ? q : 0) * R * RECB;
+    // ---- head: target row as packed pairs, minus the later actions whose u_i is not zero
+    int acc[S][5];
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < S; j++)
+#pragma unroll
+            for (int p = 0; p < 5; p++) {
+                const int e0 = 9 * j + 2 * p; // entries e0, e0 + 1 of the row (the fifth pair of a run holds one entry)
+                if constexpr (TGT16) {
+                    uint32_t pr;
+                    if ((e0 & 1) == 0)
+                        pr = tw[e0 >> 1];
+                    else
+                        pr = __byte_perm(tw[e0 >> 1], tw[(e0 >> 1) + 1 < TW ? (e0 >> 1) + 1 : e0 >> 1], 0x5432);
+                    // two's complement halves -> lo + 65536 * hi (a negative low half borrows from the high one); the fifth
+                    // pair of a run holds a single entry
+                    acc[j][p] = p < 4 ? (int)(pr - ((pr & 0x8000u) << 1)) : (int)(short)(pr & 0xFFFFu);
+                } else {
+                    auto ent = [&](int e) -> int {
+                        switch (e & 3) {
+                        case 0: return sx<0>(tw[e >> 2]);
+                        case 1: return sx<1>(tw[e >> 2]);
+                        case 2: return sx<2>(tw[e >> 2]);
+                        default: return sx<3>(tw[e >> 2]);
+                        }
+                    };
+                    acc[j][p] = p < 4 ? ent(e0) + ent(e0 + 1) * 65536 : ent(e0);
+                }
+            }
+        // bit x of mask: action a + 1 + x has u_i != 0
+        uint32_t mask = 0;
+        for (int j = a + 1, x = 0; j < R; j++, x++)
+            if (reinterpret_cast<const int8_t *>(rbase + (size_t)j * RECB)[20 + i] != 0) mask |= 1u << x;
+        if (R - 1 - a > 32) mask = 0xFFFFFFFFu; // longer lists: plain walk below
+        auto apply = [&](int j) {
+            const uint8_t *rec = rbase + (size_t)j * RECB;
+            const uint4 w03 = *reinterpret_cast<const uint4 *>(rec), w47 = *reinterpret_cast<const uint4 *>(rec + 16);
+            const uint2 w89 = *reinterpret_cast<const uint2 *>(rec + 32);
+            const int nu = -(int)reinterpret_cast<const int8_t *>(rec)[20 + i];
+            // v coefficients: record bytes 29..37 = w47.w bytes 1..3, w89.x bytes 0..3, w89.y bytes 0..1
+            const int c[S] = {nu * sx<1>(w47.w), nu * sx<2>(w47.w), nu * sx<3>(w47.w), nu * sx<0>(w89.x), nu * sx<1>(w89.x),
+                              nu * sx<2>(w89.x), nu * sx<3>(w89.x), nu * sx<0>(w89.y), nu * sx<1>(w89.y)};
+            const int pw[5] = {(int)w03.x, (int)w03.y, (int)w03.z, (int)w03.w, (int)w47.x};
+#pragma unroll
+            for (int j2 = 0; j2 < S; j2++)
+#pragma unroll
+                for (int p = 0; p < 5; p++) acc[j2][p] += c[j2] * pw[p];
+        };
+        if (R - 1 - a <= 32) {
+            while (mask) {
+                const int x = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                apply(a + 1 + x);
+            }
+        } else {
+            for (int j = a + 1; j < R; j++) apply(j);
+        }
+    }
+    // ---- slots, one at a time through the warp tile
+    const long long b = b0 + (owner ? q : 0);
+    const int hi = min(a + dim_t, R);
+    for (int s = 0; s < dim_t; s++) {
+        float *gdst = states + (b * dim_t + s) * (long long)S3;
+        const int ph = (int)((reinterpret_cast<uintptr_t>(gdst) >> 2) & 3); // the piece sits at the same offset modulo 16 bytes
+        float *row = s_tile + q * PIECE + ph + i * S2;
+        if (owner) {
+            if (live && s == 0) {
+#pragma unroll
+                for (int j = 0; j < S; j++)
+#pragma unroll
+                    for (int p = 0; p < 5; p++) {
+                        const int x = acc[j][p];
+                        if (p < 4) {
+                            const int lo = (int)(short)(x & 0xFFFF);
+                            row[9 * j + 2 * p] = (float)lo;
+                            row[9 * j + 2 * p + 1] = (float)((x - lo) >> 16);
+                        } else {
+                            row[9 * j + 8] = (float)x;
+                        }
+                    }
+            } else if (live && hi - s >= a + 1) {
+                const uint8_t *rec = rbase + (size_t)(hi - s) * RECB;
+                const uint4 w03 = *reinterpret_cast<const uint4 *>(rec), w47 = *reinterpret_cast<const uint4 *>(rec + 16);
+                const uint2 w89 = *reinterpret_cast<const uint2 *>(rec + 32);
+                const int u = (int)reinterpret_cast<const int8_t *>(rec)[20 + i];
+                const float cf[S] = {(float)(u * sx<1>(w47.w)), (float)(u * sx<2>(w47.w)), (float)(u * sx<3>(w47.w)),
+                                     (float)(u * sx<0>(w89.x)), (float)(u * sx<1>(w89.x)), (float)(u * sx<2>(w89.x)),
+                                     (float)(u * sx<3>(w89.x)), (float)(u * sx<0>(w89.y)), (float)(u * sx<1>(w89.y))};
+                // w back from the pairs: lo + 65536 * hi
+                float wf[S];
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int x = p == 0 ? (int)w03.x : (p == 1 ? (int)w03.y : (p == 2 ? (int)w03.z : (int)w03.w));
+                    const int lo = (int)(short)(x & 0xFFFF);
+                    wf[2 * p] = (float)lo, wf[2 * p + 1] = (float)((x - lo) >> 16);
+                }
+                wf[8] = (float)(int)w47.x;
+#pragma unroll
+                for (int j = 0; j < S; j++)
+#pragma unroll
+                    for (int k = 0; k < S; k++) row[9 * j + k] = cf[j] * wf[k];
+            } else {
+#pragma unroll
+                for (int e = 0; e < S2; e++) row[e] = 0.f;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        // copy-out: lane 9 x leads sample x: aligned body by TMA, up to three floats at either end by lanes 9x+1 .. 9x+6
+        if (owner) {
+            const int hc = (4 - ph) & 3, nbody = (S3 - hc) & ~3, tail = S3 - hc - nbody;
+            const float *piece = s_tile + q * PIECE + ph;
+            if (i == 0) {
+                bulk_s2g(gdst + hc, piece + hc, (uint32_t)nbody * 4u);
+                bulk_commit();
+            } else if (i <= 3) {
+                if (i - 1 < hc) gdst[i - 1] = piece[i - 1];
+            } else if (i <= 6) {
+                if (i - 4 < tail) gdst[hc + nbody + i - 4] = piece[hc + nbody + i - 4];
+            }
+            if (i == 0) bulk_wait_read<0>();
+        }
+        __syncwarp(); // the tile may be rewritten
+    }
+    if (live) {
+        if (i == 0) {
+            scalars[b] = (float)(R - a);
+            rewards[b] = -(float)(a + 1);
+        }
+#pragma unroll
+        for (int x = 0; x < 3; x++) actions[b * 27 + i * 3 + x] = (long long)own[x];
+    }
+}
+} // namespace rows9
+
 // step-major tape [R][N][TP] -> demo-major records [N][R][TP], 16 bytes per thread
 __global__ void tape_to_demo_major_kernel(const uint4 *__restrict__ src, long long src_step_stride16, uint4 *__restrict__ dst,
                                           long long N, int R, int tp16) {
@@ -694,6 +925,25 @@ int tg_demo_sample_dm(const uint8_t *tape_dm, const void *targets, int targets_i
     // target_bound + R * cmax^3 fits an int16 lane
     const long long cmax = replay_shift > 8 - replay_shift ? replay_shift : 8 - replay_shift;
     const bool pack16 = (long long)target_bound + (long long)R * cmax * cmax * cmax <= 32767;
+    if (S == 9 && pack16 && (long long)tg::rows9::WARPS * tg::rows9::warp_bytes(R) <= 200 * 1024) {
+        // 9x9x9: one thread per (sample, row), three samples per warp
+        const int smem = tg::rows9::WARPS * tg::rows9::warp_bytes(R);
+        const long long per_cta = (long long)tg::rows9::WARPS * tg::rows9::SPW;
+        const unsigned grid = (unsigned)((nb + per_cta - 1) / per_cta);
+        if (targets_i16) {
+            auto kern = tg::rows9::demo_sample_rows9_kernel<true, true>;
+            TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            kern<<<grid, 32 * tg::rows9::WARPS, smem, st>>>(tape_dm, (const uint8_t *)targets, N, R, dim_t, replay_shift, (const long long *)idx,
+                                                            nb, states, scalars, (long long *)actions, rewards);
+        } else {
+            auto kern = tg::rows9::demo_sample_rows9_kernel<false, true>;
+            TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            kern<<<grid, 32 * tg::rows9::WARPS, smem, st>>>(tape_dm, (const uint8_t *)targets, N, R, dim_t, replay_shift, (const long long *)idx,
+                                                            nb, states, scalars, (long long *)actions, rewards);
+        }
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
     TG_SWITCH_S(S, {
         const int rc = tg::launch_demo_sample_dm<kS>(tape_dm, (const uint8_t *)targets, targets_i16 != 0, pack16, N, R, dim_t, replay_shift,
                                                      (const long long *)idx, nb, states, scalars, (long long *)actions, rewards, st);

@@ -31,9 +31,9 @@ constexpr int WARPS = 4;             // games per CTA
 constexpr int TS_PITCH = 48;         // bytes per row of halves (16 halves + pad: conflict-free ldmatrix rows)
 constexpr int TS_BYTES = 82 * TS_PITCH; // 81 rows + one all-zero row = 3936
 constexpr int ZS_PITCH = 208;        // bytes per row a of Z (104 halves >= 96; 52 words: conflict-free transposed reads)
-constexpr int ZS_BYTES = 16 * ZS_PITCH; // 3328
+constexpr int ZS_BYTES = 10 * ZS_PITCH; // rows a = 0..8 and one all-zero row (a = 9..15 all read it) = 2080
 constexpr int MS_BYTES = 256;        // the game's three 9x9 int8 matrices (243 bytes at any byte alignment)
-constexpr int WARP_BYTES = TS_BYTES + ZS_BYTES + MS_BYTES; // 7520
+constexpr int WARP_BYTES = TS_BYTES + ZS_BYTES + MS_BYTES; // 6272
 static_assert(TS_BYTES >= 1536 && WARP_BYTES % 16 == 0, "the output stage overlays the T rows");
 
 constexpr float MAGIC = 12582912.0f; // 1.5 * 2^23: float(MAGIC + n) has n in its low mantissa bits
@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(32 * WARPS)
             raw[q][0] = raw[q][1] = raw[q][2] = 0;
         }
     }
-    // zero row of T, rows a = 9..15 of Z (their A-operand columns are zero, but 0 * NaN is not)
+    // zero row of T, zero row of Z for a = 9..15 (their A-operand columns are zero, but 0 * NaN is not)
     if (lane < 3) reinterpret_cast<uint4 *>(s_t + 81 * TS_PITCH)[lane] = make_uint4(0, 0, 0, 0);
-    for (int x = lane; x < 7 * ZS_PITCH / 16; x += 32) reinterpret_cast<uint4 *>(s_z + 9 * ZS_PITCH)[x] = make_uint4(0, 0, 0, 0);
+    if (lane < ZS_PITCH / 16) reinterpret_cast<uint4 *>(s_z + 9 * ZS_PITCH)[lane] = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint32_t *>(s_m)[lane] = m0;
     reinterpret_cast<uint32_t *>(s_m)[32 + lane] = m1;
 
@@ -167,10 +167,8 @@ __global__ void __launch_bounds__(32 * WARPS)
         uint16_t *zr = zrow + a * (ZS_PITCH / 2);
         zr[9 * g + 2 * t] = (uint16_t)p0, zr[9 * g + 2 * t + 1] = (uint16_t)(p0 >> 16); // j' = g, k' = 2t, 2t+1
         if (g == 0) *reinterpret_cast<uint32_t *>(zr + 72 + 2 * t) = p1;               // j' = 8
-        if (t == 0) {
-            zr[9 * g + 8] = (uint16_t)p2;                                                 // j' = g, k' = 8
-            if (g == 0) zr[80] = (uint16_t)(p2 >> 16);                                    // j' = 8, k' = 8
-        }
+        if (t == 0) zr[9 * g + 8] = (uint16_t)p2;                                       // j' = g, k' = 8
+        if (lane == 0) zr[80] = (uint16_t)(p2 >> 16);                                   // j' = 8, k' = 8
     }
     {
         const float ym = fmaxf(__low2float(ymax), __high2float(ymax)), zm = fmaxf(__low2float(zmax), __high2float(zmax));
@@ -184,7 +182,7 @@ __global__ void __launch_bounds__(32 * WARPS)
 
     // ---- 3. eleven N tiles over n = 9 j' + k'; accumulator (row i', cols n, n+1) is slab entry i' * 84 + n
     uint32_t over = 0;
-    const int zl_row = (lane & 7) + 8 * ((lane >> 3) & 1), zl_col = (lane >> 4) * 16; // ldmatrix.trans: rows a, 16 bytes of columns
+    const int zl_row = min((lane & 7) + 8 * ((lane >> 3) & 1), 9), zl_col = (lane >> 4) * 16; // ldmatrix.trans: rows a (9 = the zero row), 16 bytes of columns
 #pragma unroll
     for (int tp = 0; tp < 6; tp++) {
         uint32_t zb[4];

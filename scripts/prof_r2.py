@@ -1,0 +1,34 @@
+"""One launch set of a round-2 kernel at bench size (for ncu): python scripts/prof_r2.py sample|basis9|basis16|basis4|demo9|demo4"""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from mat_mul_b200 import env
+V5, P5 = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05)
+which = sys.argv[1]
+if which == "sample":
+    S, R, N = 9, 23, 1 << 18
+    tape, slab, _ = env.make_synthetic_demos(N, R, S, V5, P5, 2, seed=1)
+    store = env.DemoStore.from_tape(tape, slab, S, 2)
+    idx = torch.randint(0, N * R, (1 << 16,), device="cuda")
+    for _ in range(3):
+        store.samples(idx, 2, replay_shift=2)
+elif which.startswith("basis"):
+    S = int(which[5:])
+    R, N = {4: (7, 1 << 20), 9: (23, 1 << 18), 16: (49, 1 << 17)}[S]
+    _, slab, _ = env.make_synthetic_demos(N, R, S, V5, P5, 2, seed=1)
+    mats = env.sample_unimodular(N, S, seed=3, p_nonzero=0.3)
+    out = torch.empty(slab.shape, dtype=torch.int16, device="cuda")
+    for _ in range(3):
+        env.change_of_basis(slab, mats, S, out=out)
+elif which.startswith("demo"):
+    S = int(which[4:])
+    R, N = {4: (7, 1 << 22), 9: (23, 1 << 20), 16: (49, 1 << 17)}[S]
+    vals, probs, shift = ((-1, 0, 1), (0.15, 0.7, 0.15), 1) if S == 4 else (V5, P5, 2)
+    lay = env.layout(S)
+    tape = torch.empty((R, N, lay.token_pitch), dtype=torch.uint8, device="cuda")
+    slab = torch.empty((N, lay.game_pitch), dtype=torch.int8, device="cuda")
+    for _ in range(3):
+        env.make_synthetic_demos(N, R, S, vals, probs, shift, seed=1, tape=tape, slab=slab)
+torch.cuda.synchronize()
+print("ok")
