@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(SampleCfg<S>::NT)
 // floats is 81 consecutive words of the tile and lanes are 81 words apart: conflict-free for the lanes of one sample.
 namespace rows9 {
 constexpr int S = 9, S2 = 81, S3 = 729, TP = 32, RP = 84, GP = 768;
-constexpr int WARPS = 3, SPW = 3;            // warps per CTA; samples per warp (27 of 32 lanes own a row)
+constexpr int WARPS = 4, SPW = 3;            // warps per CTA; samples per warp (27 of 32 lanes own a row)
 constexpr int RECB = 48;                     // replay record: 5 words pack16(w) | 5 words coefficient bytes (u 0..8, v 9..17) | pad
 constexpr int PIECE = 736;                   // floats per sample in the warp tile (729 + alignment phase, multiple of 4 and of 32)
 __host__ __device__ constexpr int warp_bytes(int R) { return ((SPW * R * RECB + 15) & ~15) + SPW * PIECE * 4; }
@@ -490,7 +490,7 @@ template <int B>
 __device__ __forceinline__ int sx(uint32_t w) { return sext_byte<B>(w); }
 
 template <bool TGT16, bool PACK16>
-__global__ void __launch_bounds__(32 * WARPS, 6)
+__global__ void __launch_bounds__(32 * WARPS, 4)
     demo_sample_rows9_kernel(const uint8_t *__restrict__ tape_dm, const uint8_t *__restrict__ targets, long long N, int R, int dim_t,
                              int replay_shift, const long long *__restrict__ idx, long long nb, float *__restrict__ states,
                              float *__restrict__ scalars, long long *__restrict__ actions, float *__restrict__ rewards) {
@@ -499,19 +499,29 @@ __global__ void __launch_bounds__(32 * WARPS, 6)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *s_rec = smem + (size_t)warp * warp_bytes(R);
     float *s_tile = reinterpret_cast<float *>(s_rec + ((SPW * R * RECB + 15) & ~15));
-    const long long b0 = ((long long)blockIdx.x * WARPS + warp) * SPW;
-    if (b0 >= nb) return;
-    const int ns = (int)min((long long)SPW, nb - b0);
-    // ---- the warp's samples: lane q < ns reads index q; everybody gets (demo, a) of every sample by shuffle
+    // a warp walks triples of samples trip, trip + nwarps, ...: the index of the NEXT triple is read while this one is
+    // processed, and its records and target rows are pulled into L2 before the slots of this one are built, so that the
+    // two dependent DRAM round trips at the head of a triple (index -> records / targets) are hidden behind the previous one
+    const long long nwarps = (long long)gridDim.x * WARPS, ntrip = (nb + SPW - 1) / SPW;
+    long long trip = (long long)blockIdx.x * WARPS + warp;
+    if (trip >= ntrip) return;
+    auto decode = [&](long long id, long long &dm, int &aa) {
+        dm = -1, aa = -1;
+        if (id >= 0) {
+            split_index(id, R, dm, aa);
+            if (dm >= N) dm = -1, aa = -1;
+        }
+    };
     long long my_demo = -1;
     int my_a = -1;
-    if (lane < ns) {
-        const long long id = idx[b0 + lane];
-        if (id >= 0) {
-            split_index(id, R, my_demo, my_a);
-            if (my_demo >= N) my_demo = -1, my_a = -1;
-        }
-    }
+    if (lane < (int)min((long long)SPW, nb - trip * SPW)) decode(idx[trip * SPW + lane], my_demo, my_a);
+    for (;;) {
+    const long long b0 = trip * SPW;
+    const int ns = (int)min((long long)SPW, nb - b0);
+    const long long ntr = trip + nwarps;
+    long long nid = -1;
+    if (ntr < ntrip && lane < (int)min((long long)SPW, nb - ntr * SPW)) nid = idx[ntr * SPW + lane];
+    // ---- the warp's samples: lane q < ns holds sample q; everybody gets (demo, a) of every sample by shuffle
     long long demo_q[SPW];
     int a_q[SPW];
 #pragma unroll
@@ -622,6 +632,20 @@ __global__ void __launch_bounds__(32 * WARPS, 6)
             for (int j = a + 1; j < R; j++) apply(j);
         }
     }
+    // ---- the next triple: decode its indices (read at the top) and pull its records and target rows into L2
+    long long nx_demo;
+    int nx_a;
+    decode(nid, nx_demo, nx_a);
+    {
+        const long long pd = __shfl_sync(0xFFFFFFFFu, nx_demo, q < SPW ? q : 0);
+        const int pa = __shfl_sync(0xFFFFFFFFu, nx_a, q < SPW ? q : 0);
+        if (q < SPW && pa >= 0) {
+            const uint8_t *trow = targets + ((size_t)pd * GP + i * RP) * (TGT16 ? 2 : 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(trow));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(trow + (TGT16 ? 161 : 83)));
+            if (i * 128 < (R - pa) * TP) asm volatile("prefetch.global.L2 [%0];" ::"l"(tape_dm + ((size_t)pd * R + pa) * TP + i * 128));
+        }
+    }
     // ---- slots, one at a time through the warp tile
     const long long b = b0 + (owner ? q : 0);
     const int hi = min(a + dim_t, R);
@@ -696,6 +720,10 @@ __global__ void __launch_bounds__(32 * WARPS, 6)
 #pragma unroll
         for (int x = 0; x < 3; x++) actions[b * 27 + i * 3 + x] = (long long)own[x];
     }
+    if (ntr >= ntrip) break;
+    trip = ntr, my_demo = nx_demo, my_a = nx_a;
+    __syncwarp(); // the records of this triple are dead: the next conversion may overwrite them
+    } // triples
 }
 } // namespace rows9
 
@@ -929,7 +957,8 @@ int tg_demo_sample_dm(const uint8_t *tape_dm, const void *targets, int targets_i
         // 9x9x9: one thread per (sample, row), three samples per warp
         const int smem = tg::rows9::WARPS * tg::rows9::warp_bytes(R);
         const long long per_cta = (long long)tg::rows9::WARPS * tg::rows9::SPW;
-        const unsigned grid = (unsigned)((nb + per_cta - 1) / per_cta);
+        const long long want = (nb + per_cta - 1) / per_cta;
+        const unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4); // persistent warps: four CTAs per SM
         if (targets_i16) {
             auto kern = tg::rows9::demo_sample_rows9_kernel<true, true>;
             TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
