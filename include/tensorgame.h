@@ -130,19 +130,31 @@ int tg_replay(const int8_t *slab_in, const uint8_t *tape, int64_t tape_step_stri
  * is the byte distance between consecutive steps (N_total*TP), so a rank can
  * write its shard of demos straight into a larger tape.
  *
- * Throughput mode (device RNG; contract in DESIGN.md, restated by the oracle):
+ * Throughput mode (device RNG; contracts in DESIGN.md, restated by the oracle):
  * demo d = first_demo + n draws its R factor triples from Philox4x32-10 keyed
- * by seed with counter (d_lo, d_hi, term | try << 16, block): 15-bit draws
- * against floor(cdf * 2^15) of `probs` over `values` (HOST arrays,
- * n_values <= 8, values in [-shift, shift], max_tries <= 65535); a triple is rejected iff
- * u, v or w is all zero (utils.py:229), at most max_tries tries per term
- * (TG_FLAG_EXHAUSTED).  Writes tokens (values + shift) to the tape, the summed
+ * by seed.  `values` / `probs` are HOST arrays, n_values <= 8, values in
+ * [-shift, shift].
+ *  v2 (n_values <= 5 and P(0) <= 0.999) "group alias": an accepted triple of the
+ *   reference's rejection loop is three independent factors, each conditioned on
+ *   being non-zero; that conditional distribution is sampled directly, three
+ *   entries at a time, from alias tables of 128 buckets (tg_demo_alias_tables)
+ *   with one 16-bit draw per group, counter (d_lo, d_hi, term, block).  No tries:
+ *   max_tries does not apply and TG_FLAG_EXHAUSTED is never raised.
+ *  v1 (other alphabets): counter (d_lo, d_hi, term | try << 16, block), 15-bit
+ *   draws against floor(cdf * 2^15); a triple is rejected iff u, v or w is all
+ *   zero (utils.py:229), at most max_tries <= 65535 tries per term
+ *   (TG_FLAG_EXHAUSTED).
+ * Writes tokens (values + shift) to the tape, the summed
  * target tensors to slab [N][GP] and TG_FLAG_RANGE/EXHAUSTED to flags (may be
  * NULL).  Replaces utils.py:203-233 and datasets.py:124-142 (different RNG
  * stream than torch: see tg_demo_from_ustream for same-seed parity). */
 int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int S, int shift, const int8_t *values,
                        const double *probs, int n_values, int max_tries, uint8_t *tape, int64_t tape_step_stride,
                        int8_t *slab, uint8_t *flags, void *stream);
+/* HOST function: the alias tables of contract v2 as uint16 [8][128] -- [0] the plain distribution of a group of three
+ * entries, [1] of a single entry, [2 + g] the tilted table of group g; bucket = 9-bit threshold | alias outcome << 9.
+ * TG_E_ARG where v2 does not apply. */
+int tg_demo_alias_tables(const int8_t *values, const double *probs, int n_values, int S, uint16_t *tables_host);
 /* slab[n] = sum_r rank1(tape[r][n]) -- the target tensor of a given action
  * list (utils.py:40-53 uvw_to_demo, utils.py:232, datasets.py:141). */
 int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,

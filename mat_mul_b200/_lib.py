@@ -105,6 +105,7 @@ _SIGNATURES = {
     "tg_replay": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "tg_demo_gen_philox": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int,
                                      _vp, C.c_int64, _vp, _vp, _vp]),
+    "tg_demo_alias_tables": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "tg_demo_accumulate": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "tg_demo_accumulate_tc": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "tg_demo_sample": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp,

@@ -29,6 +29,8 @@
 //      R * shift^3 a per-thread bound shift^2 * sum_r |v_rj| guards the packed
 //      path and the (rare) thread above it recomputes its entries one by one.
 //   C. the slab tile leaves through one TMA bulk store.
+#include <cstring>
+
 #include "tg_demo_mma.cuh"
 #include "tg_step.cuh"
 
@@ -64,6 +66,83 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
+}
+
+// ---- contract v2: the "group alias" sampler (restated by oracle/tg_oracle.c orc_demo_philox_v2).
+// An accepted triple of the reference's rejection loop (utils.py:222-232) is three independent factors, each an i.i.d.
+// factor conditioned on being non-zero; that conditional distribution is sampled DIRECTLY, group of three entries by group
+// of three entries, from alias tables of 128 buckets: one 16-bit draw per group (bucket = draw & 127, keep the bucket's own
+// outcome iff draw >> 7 < its 9-bit threshold, else its alias), while all groups so far are zero from the table tilted by
+// the probability that the rest of the factor is zero too.  No rejection loop, half the Philox blocks of the thresholded
+// contract, and no comparisons per token.
+constexpr int ALIAS_BUCKETS = 128;
+struct AliasParams {
+    uint16_t tab[8][ALIAS_BUCKETS]; // [g] tilted table of group g (g < NG <= 6), [6] plain size 3, [7] plain size 1
+    uint32_t lut3[ALIAS_BUCKETS];   // outcome of a size-3 group -> its three tokens (bytes 0..2)
+    uint32_t lut1[8];               // outcome of a size-1 group -> its token
+    uint32_t zo3, zo1;              // the all-zero outcomes (255 if 0 is not in the alphabet)
+    uint32_t rk[10][2];             // Philox round keys
+};
+template <int S>
+struct AliasGeo {
+    static constexpr int NG = (S + 2) / 3, LAST = S - 3 * (NG - 1); // groups per factor, size of the last one (1 or 3)
+    static constexpr int ND = 3 * NG, NB = (ND + 7) / 8;             // 16-bit draws and Philox blocks per triple
+    static constexpr int TAB_WORDS = (NG + 2) * ALIAS_BUCKETS / 2;   // shared-memory copy: tables [0..NG), plain 3, plain 1
+    static constexpr int SMEM_BYTES = TAB_WORDS * 4 + ALIAS_BUCKETS * 4 + 32;
+    static_assert(LAST == 1 || LAST == 3, "group sizes 3 and 1 only");
+};
+
+// CTA-wide copy of the tables from the kernel parameters (constant bank) to shared memory
+template <int S, int NT>
+__device__ __forceinline__ void alias_to_smem(const AliasParams &ap, uint32_t *s_alias) {
+    using A = AliasGeo<S>;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ap.tab);
+    for (int w = threadIdx.x; w < A::NG * (ALIAS_BUCKETS / 2); w += NT) s_alias[w] = src[w];
+    for (int w = threadIdx.x; w < ALIAS_BUCKETS; w += NT) s_alias[A::NG * (ALIAS_BUCKETS / 2) + w] = src[6 * (ALIAS_BUCKETS / 2) + w]; // plain 3, plain 1
+    for (int w = threadIdx.x; w < ALIAS_BUCKETS + 8; w += NT) s_alias[A::TAB_WORDS + w] = w < ALIAS_BUCKETS ? ap.lut3[w] : ap.lut1[w - ALIAS_BUCKETS];
+}
+
+// one factor triple (3S tokens) of demo (d_lo, d_hi), term r under contract v2
+template <int S>
+__device__ __forceinline__ void draw_triple_alias(uint32_t words[(3 * S + 3) / 4], uint32_t d_lo, uint32_t d_hi, int r,
+                                                  const AliasParams &ap, const uint32_t *s_alias) {
+    using A = AliasGeo<S>;
+    constexpr int NW = (3 * S + 3) / 4;
+    const uint16_t *s_tab = reinterpret_cast<const uint16_t *>(s_alias);
+    const uint32_t *s_lut3 = s_alias + A::TAB_WORDS, *s_lut1 = s_lut3 + ALIAS_BUCKETS;
+    uint32_t blk[4 * A::NB];
+#pragma unroll
+    for (int b = 0; b < A::NB; b++) {
+        uint32_t c0 = d_lo, c1 = d_hi, c2 = (uint32_t)r, c3 = (uint32_t)b;
+#pragma unroll
+        for (int q = 0; q < 10; q++) {
+            const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+            c0 = (uint32_t)(p1 >> 32) ^ c1 ^ ap.rk[q][0], c1 = (uint32_t)p1, c2 = (uint32_t)(p0 >> 32) ^ c3 ^ ap.rk[q][1], c3 = (uint32_t)p0;
+        }
+        blk[4 * b] = c0, blk[4 * b + 1] = c1, blk[4 * b + 2] = c2, blk[4 * b + 3] = c3;
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) words[w] = 0;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+        bool az = true; // every group of this factor so far is all zero
+#pragma unroll
+        for (int g = 0; g < A::NG; g++) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int m = f * A::NG + g;
+            const uint32_t h = (m & 1) ? (blk[m >> 1] >> 16) : (blk[m >> 1] & 0xFFFFu);
+            const bool three = g < A::NG - 1 || A::LAST == 3;
+            const int plain = three ? A::NG : A::NG + 1;
+            const uint32_t bucket = s_tab[(az ? g : plain) * ALIAS_BUCKETS + (h & 127u)];
+            const uint32_t o = ((h >> 7) < (bucket & 511u)) ? (h & 127u) : (bucket >> 9);
+            const uint32_t tk = three ? s_lut3[o] : s_lut1[o];
+            az = az && (o == (three ? ap.zo3 : ap.zo1));
+            const int B = f * S + 3 * g; // byte offset of the group in the record
+            words[B >> 2] |= tk << (8 * (B & 3));
+            if ((B & 3) + (three ? 3 : 1) > 4) words[(B >> 2) + 1] |= tk >> (32 - 8 * (B & 3));
+        }
+    }
 }
 
 template <int S, int NT, int NPASS = 1>
@@ -184,11 +263,13 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
 // MMA = KS > 0 (16x16x16, R <= 16 KS): phase A also leaves the raw 48-byte action records in shared memory and every warp
 // then sums the targets of its demos on the tensor cores (tg_demo_mma.cuh) -- CTAs of one SM are in different phases, so
 // the sampler's integer work and the MMAs overlap.
-template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD, int MMA = 0>
+// ALIAS: phase A draws under contract v2 (group alias tables, no rejection loop); the categorical thresholds are unused.
+template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD, int MMA = 0, bool ALIAS = false>
 __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 5 : 4))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
-                long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags) {
+                long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags,
+                const __grid_constant__ AliasParams ap) {
     using C = DemoCfg<S, NT, NPASS>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -198,7 +279,8 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     constexpr int MMA_SCRATCH = MMA > 0 ? (NT / 32) * acc16::WARP_WORDS * 4 : 0; // per-warp H and U2 tables
     uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (MMA == 0 ? C::main_bytes(R) : MMA > 0 ? C::rec_region(R) + MMA_SCRATCH : 0)); // [TG]
     uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
-    uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16)
+    uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16); ALIAS: the tables live here instead
+    uint32_t *s_alias = s_list;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -208,9 +290,31 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
 
     for (int g = tid; g < C::TG; g += NT) s_flag[g] = 0;
     if (tid < 3) s_work[tid] = 0;
+    if constexpr (ALIAS) alias_to_smem<S, NT>(ap, s_alias);
     __syncthreads();
 
-    if constexpr (SAMPLE) {
+    if constexpr (SAMPLE && ALIAS) {
+        // ---------------- A (contract v2). every (demo, term) pair is one draw: no tries, no retry lists
+        for (int p = tid; p < npairs; p += NT) {
+            const int g = magic_r ? (int)__umulhi((uint32_t)p, magic_r) : p; // p / R
+            const int r = p - g * R;
+            const unsigned long long d = first_demo + (unsigned long long)(g0 + g);
+            uint32_t words[G::TP / 4];
+#pragma unroll
+            for (int w = C::NW; w < G::TP / 4; w++) words[w] = 0;
+            draw_triple_alias<S>(words, (uint32_t)d, (uint32_t)(d >> 32), r, ap, s_alias);
+            uint4 *dst = reinterpret_cast<uint4 *>(tape + (size_t)r * tape_step_stride + (g0 + g) * G::TP);
+#pragma unroll
+            for (int w = 0; w < G::TP / 16; w++) dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
+            if constexpr (MMA == 0) {
+                emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+            } else if constexpr (MMA > 0) {
+                uint4 *rdst = reinterpret_cast<uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
+#pragma unroll
+                for (int w = 0; w < G::TP / 16; w++) rdst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
+            }
+        }
+    } else if constexpr (SAMPLE) {
         // ---------------- A. draw the factor triples of the tile.
         // A1: every lane runs a (pair, try) state machine: a rejected triple just bumps the lane's try, an accepted
         // one is stored and the lane takes the next fresh pair (one atomic per warp and round) -- all 32 lanes draw in
@@ -541,14 +645,15 @@ static int launch_demo(unsigned long long first, long long N, int R, int shift, 
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R); // ceil(2^32 / R)
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+    static const AliasParams no_alias = {};
     if (guard) {
         auto kern = demo_kernel<S, NT, NPASS, SAMPLE, NTHR, true>;
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
+        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags, no_alias);
     } else {
         auto kern = demo_kernel<S, NT, NPASS, SAMPLE, NTHR, false>;
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
+        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags, no_alias);
     }
     TG_CUDA(cudaGetLastError());
     return TG_OK;
@@ -564,11 +669,127 @@ static int launch_demo16_mma(unsigned long long first, long long N, int R, int s
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+    static const AliasParams no_alias = {};
     auto kern = demo_kernel<16, NT, NPASS, true, NTHR, false, MMA>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags);
+    kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags, no_alias);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
+}
+
+// ---- contract v2 launches (the measured-best tile shapes of each size, phase A on the alias tables)
+template <int S, int NT, int NPASS, int MMA>
+static int launch_demo_alias(unsigned long long first, long long N, int R, int shift, const Categorical &cat, const AliasParams &ap,
+                             uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
+    using C = DemoCfg<S, NT, NPASS>;
+    constexpr int TAIL = (2 * NT * 4 > AliasGeo<S>::SMEM_BYTES ? 2 * NT * 4 : AliasGeo<S>::SMEM_BYTES);
+    const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : C::main_bytes(R)) + C::TG * 4 + 16 + TAIL;
+    if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
+    const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
+    const long long grid = (N + C::TG - 1) / C::TG;
+    if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+    const bool guard = MMA == 0 && (long long)R * shift * shift * shift > 191;
+    if (guard) {
+        auto kern = demo_kernel<S, NT, NPASS, true, 2, true, MMA, true>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, 1, tape, stride, slab, flags, ap);
+    } else {
+        auto kern = demo_kernel<S, NT, NPASS, true, 2, false, MMA, true>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, 1, tape, stride, slab, flags, ap);
+    }
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+static int dispatch_demo_alias(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
+                               const AliasParams &ap, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
+    switch (S) {
+    case 4:
+        if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
+            return launch_demo_alias<4, 256, 4, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        return launch_demo_alias<4, 256, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+    case 9: return launch_demo_alias<9, 128, 2, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+    case 16:
+        if (demo_acc16_mma_applies(R)) {
+            if (R <= 32) return launch_demo_alias<16, 128, 2, 2>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+            return launch_demo_alias<16, 128, 2, 4>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        }
+        return launch_demo_alias<16, 128, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+    }
+    return TG_E_ARG;
+}
+
+// ---- host side of contract v2: Vose's alias construction, in exactly the order the oracle restates
+static void vose128(const double *P, int count, uint16_t *out) {
+    double sc[ALIAS_BUCKETS], prob[ALIAS_BUCKETS];
+    int alias[ALIAS_BUCKETS], small[ALIAS_BUCKETS], large[ALIAS_BUCKETS], ns = 0, nl = 0;
+    for (int o = 0; o < ALIAS_BUCKETS; o++) sc[o] = (o < count ? P[o] : 0.0) * (double)ALIAS_BUCKETS, alias[o] = o, prob[o] = 1.0;
+    for (int o = 0; o < ALIAS_BUCKETS; o++) (sc[o] < 1.0 ? small[ns++] : large[nl++]) = o;
+    while (ns > 0 && nl > 0) {
+        const int sm = small[--ns], lg = large[--nl];
+        prob[sm] = sc[sm], alias[sm] = lg;
+        sc[lg] = (sc[lg] + sc[sm]) - 1.0;
+        (sc[lg] < 1.0 ? small[ns++] : large[nl++]) = lg;
+    }
+    for (int o = 0; o < ALIAS_BUCKETS; o++) {
+        const double q = prob[o] < 0.0 ? 0.0 : (prob[o] > 1.0 ? 1.0 : prob[o]);
+        uint32_t thr = (uint32_t)(q * 512.0 + 0.5);
+        int al = alias[o];
+        if (thr >= 512u) thr = 511u, al = o; // probability one: either branch gives the bucket's own outcome
+        out[o] = (uint16_t)(thr | ((uint32_t)al << 9));
+    }
+}
+
+// contract v2 applies to alphabets of at most five values whose P(0) leaves a non-zero factor reachable
+static bool alias_applies(const int8_t *values, const double *probs, int n, int S) {
+    if (n < 1 || n > 5 || !supported_S(S)) return false;
+    double total = 0, p0 = 0;
+    for (int i = 0; i < n; i++) total += probs[i];
+    for (int i = 0; i < n; i++)
+        if (values[i] == 0) p0 += probs[i] / total;
+    return p0 <= 0.999;
+}
+
+static void build_alias(const int8_t *values, const double *probs, int n, int S, int shift, uint64_t seed, AliasParams &A) {
+    double p[5], total = 0, p0 = 0;
+    int z = -1;
+    for (int i = 0; i < n; i++) total += probs[i];
+    for (int i = 0; i < n; i++) {
+        p[i] = probs[i] / total;
+        if (values[i] == 0 && z < 0) z = i, p0 = p[i];
+    }
+    const int ng = (S + 2) / 3, last = S - 3 * (ng - 1);
+    A = AliasParams{};
+    A.zo3 = z >= 0 ? (uint32_t)(z + n * z + n * n * z) : 255u;
+    A.zo1 = z >= 0 ? (uint32_t)z : 255u;
+    double P3[ALIAS_BUCKETS], P1[ALIAS_BUCKETS];
+    for (int o = 0; o < n * n * n; o++) {
+        P3[o] = (p[o % n] * p[(o / n) % n]) * p[o / (n * n)];
+        A.lut3[o] = ((uint32_t)(values[o % n] + shift) & 0xFFu) | (((uint32_t)(values[(o / n) % n] + shift) & 0xFFu) << 8) |
+                    (((uint32_t)(values[o / (n * n)] + shift) & 0xFFu) << 16);
+    }
+    for (int o = 0; o < n; o++) P1[o] = p[o], A.lut1[o] = (uint32_t)(values[o] + shift) & 0xFFu;
+    vose128(P3, n * n * n, A.tab[6]);
+    vose128(P1, n, A.tab[7]);
+    for (int g = 0; g < ng; g++) {
+        const int size = (g < ng - 1) ? 3 : last;
+        const int count = size == 3 ? n * n * n : n, zo = size == 3 ? (int)A.zo3 : (int)A.zo1;
+        double qlater = 1.0; // P(every entry after this group is zero)
+        for (int e = 3 * g + size; e < S; e++) qlater *= p0;
+        double W[ALIAS_BUCKETS], sum = 0;
+        for (int o = 0; o < count; o++) {
+            W[o] = size == 3 ? P3[o] : P1[o];
+            if (o == zo) W[o] *= (1.0 - qlater);
+            sum += W[o];
+        }
+        for (int o = 0; o < count; o++) W[o] /= sum;
+        vose128(W, count, A.tab[g]);
+    }
+    for (int r = 0; r < 10; r++) {
+        A.rk[r][0] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        A.rk[r][1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
 }
 
 template <int NTHR>
@@ -683,6 +904,12 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
         cat.rk[r][1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // contract v2 (group alias tables, no rejection loop) for alphabets of at most five values; max_tries does not apply
+    if (tg::alias_applies(values, probs, n_values, S)) {
+        tg::AliasParams ap;
+        tg::build_alias(values, probs, n_values, S, shift, seed, ap);
+        return tg::dispatch_demo_alias(first_demo, N, R, S, shift, cat, ap, tape, tape_step_stride, slab, flags, st);
+    }
     // 16x16x16, R <= 64: the targets are summed on the tensor cores (tg_demo_mma.cuh) inside the sampling kernel;
     // TG_DEMO_MMA=0 keeps the packed-IMAD accumulation (A/B timing only)
 #ifdef TG_TUNING
@@ -700,6 +927,17 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
     if (n_values <= 5)
         return tg::dispatch_demo<true, 4>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
     return tg::dispatch_demo<true, 7>(first_demo, N, R, S, shift, cat, max_tries, tape, tape_step_stride, slab, flags, st);
+}
+
+int tg_demo_alias_tables(const int8_t *values, const double *probs, int n_values, int S, uint16_t *tables_host) {
+    if (!values || !probs || !tables_host || !tg::alias_applies(values, probs, n_values, S)) return TG_E_ARG;
+    tg::AliasParams ap;
+    tg::build_alias(values, probs, n_values, S, 0, 0, ap);
+    // oracle order: [0] plain size 3, [1] plain size 1, [2 + g] tilted table of group g
+    memcpy(tables_host, ap.tab[6], sizeof(ap.tab[6]));
+    memcpy(tables_host + tg::ALIAS_BUCKETS, ap.tab[7], sizeof(ap.tab[7]));
+    memcpy(tables_host + 2 * tg::ALIAS_BUCKETS, ap.tab[0], 6 * sizeof(ap.tab[0]));
+    return TG_OK;
 }
 
 int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N, int R, int S, int shift, int8_t *slab,

@@ -664,6 +664,151 @@ void orc_demos_philox_batch(uint64_t seed, uint64_t d0, int64_t n, const int32_t
     if (exhausted) *exhausted = ex;
 }
 
+/* ---- Throughput-mode demo contract v2 (ours): the "group alias" sampler.
+ *
+ * The reference draws every entry of a factor i.i.d. from `probs` and rejects a triple iff u, v or w is all zero
+ * (utils.py:222-232).  The three factors of an accepted triple are therefore independent, each distributed as an i.i.d.
+ * factor CONDITIONED on being non-zero -- which can be sampled directly, without a rejection loop: a factor is cut into
+ * groups of three consecutive entries (the last group holds what is left: S = 4 -> 3+1, 9 -> 3+3+3, 16 -> 3*5+1), groups
+ * are drawn left to right, and while every group so far is all zero the next group is drawn from the distribution tilted
+ * by the probability that the REST of the factor can still make it non-zero:
+ *     P(x_g | all earlier groups zero) ~ P(x_g) * (x_g != 0 ? 1 : 1 - P(all later groups zero)),
+ * otherwise from the plain product distribution.  Each group distribution (<= 5^3 = 125 outcomes) is an alias table of
+ * 128 buckets (Vose's construction in the order written below), a bucket being a 9-bit threshold and an alias outcome:
+ * one 16-bit draw h picks bucket h & 127 and keeps the bucket's own outcome iff (h >> 7) < thr, else takes the alias.
+ * Outcome o of a size-3 group encodes the value indices (o % n, o / n % n, o / n^2).
+ * Draw m = f * NG + g (factor f, group g, NG groups per factor) is half m & 1 of word (m >> 1) & 3 of Philox block m >> 3
+ * with ctr = (d_lo, d_hi, r, block), key = seed.  No tries: max_tries does not apply.  Used when n_values <= 5 and
+ * P(0) <= 0.999 (orc_alias_applies); other alphabets keep the thresholded contract above. */
+#define ORC_AB 128
+typedef struct {
+    uint16_t tab[8][ORC_AB]; /* [0] plain size 3, [1] plain size 1, [2 + g] tilted table of group g */
+    int32_t ng, last, n, zo3, zo1;
+} orc_alias;
+
+static void orc_vose(const double *P, int count, uint16_t *out) {
+    double sc[ORC_AB], prob[ORC_AB];
+    int alias[ORC_AB], small[ORC_AB], large[ORC_AB], ns = 0, nl = 0;
+    for (int o = 0; o < ORC_AB; o++) {
+        sc[o] = (o < count ? P[o] : 0.0) * (double)ORC_AB;
+        alias[o] = o;
+        prob[o] = 1.0;
+    }
+    for (int o = 0; o < ORC_AB; o++) {
+        if (sc[o] < 1.0) small[ns++] = o; else large[nl++] = o;
+    }
+    while (ns > 0 && nl > 0) {
+        const int sm = small[--ns], lg = large[--nl];
+        prob[sm] = sc[sm];
+        alias[sm] = lg;
+        sc[lg] = (sc[lg] + sc[sm]) - 1.0;
+        if (sc[lg] < 1.0) small[ns++] = lg; else large[nl++] = lg;
+    }
+    for (int o = 0; o < ORC_AB; o++) {
+        double q = prob[o] < 0.0 ? 0.0 : (prob[o] > 1.0 ? 1.0 : prob[o]);
+        uint32_t thr = (uint32_t)(q * 512.0 + 0.5);
+        int al = alias[o];
+        if (thr >= 512u) thr = 511u, al = o; /* probability one: either branch gives the bucket's own outcome */
+        out[o] = (uint16_t)(thr | ((uint32_t)al << 9));
+    }
+}
+
+int orc_alias_applies(const int32_t *values, const double *probs, int n_values, int S) {
+    if (n_values < 1 || n_values > 5 || !(S == 4 || S == 9 || S == 16)) return 0;
+    double total = 0, p0 = 0;
+    for (int i = 0; i < n_values; i++) total += probs[i];
+    for (int i = 0; i < n_values; i++)
+        if (values[i] == 0) p0 += probs[i] / total;
+    return p0 <= 0.999;
+}
+
+static void orc_alias_build(const int32_t *values, const double *probs, int n, int S, orc_alias *A) {
+    double p[5], total = 0, p0 = 0;
+    int z = -1;
+    for (int i = 0; i < n; i++) total += probs[i];
+    for (int i = 0; i < n; i++) {
+        p[i] = probs[i] / total;
+        if (values[i] == 0 && z < 0) z = i, p0 = p[i];
+    }
+    memset(A, 0, sizeof(*A));
+    A->n = n, A->ng = (S + 2) / 3, A->last = S - 3 * (A->ng - 1);
+    A->zo3 = z >= 0 ? z + n * z + n * n * z : 255;
+    A->zo1 = z >= 0 ? z : 255;
+    double P3[ORC_AB], P1[ORC_AB];
+    for (int o = 0; o < n * n * n; o++) P3[o] = (p[o % n] * p[(o / n) % n]) * p[o / (n * n)];
+    for (int o = 0; o < n; o++) P1[o] = p[o];
+    orc_vose(P3, n * n * n, A->tab[0]);
+    orc_vose(P1, n, A->tab[1]);
+    for (int g = 0; g < A->ng; g++) {
+        const int size = (g < A->ng - 1) ? 3 : A->last;
+        const int count = size == 3 ? n * n * n : n, zo = size == 3 ? A->zo3 : A->zo1;
+        double qlater = 1.0; /* P(every entry after this group is zero) */
+        for (int e = 3 * g + size; e < S; e++) qlater *= p0;
+        double W[ORC_AB], sum = 0;
+        for (int o = 0; o < count; o++) {
+            W[o] = size == 3 ? P3[o] : P1[o];
+            if (o == zo) W[o] *= (1.0 - qlater);
+            sum += W[o];
+        }
+        for (int o = 0; o < count; o++) W[o] /= sum;
+        orc_vose(W, count, A->tab[2 + g]);
+    }
+}
+
+/* tables as the library's tg_demo_alias_tables writes them: uint16 [8][128] */
+void orc_alias_tables(const int32_t *values, const double *probs, int n_values, int S, uint16_t *out) {
+    orc_alias A;
+    orc_alias_build(values, probs, n_values, S, &A);
+    memcpy(out, A.tab, sizeof(A.tab));
+}
+
+static void orc_demo_philox_v2(uint64_t seed, uint64_t d, const int32_t *values, const orc_alias *A, int R, int S, int shift,
+                               int32_t *tokens_out, int32_t *target_out) {
+    const int S3 = S * S * S, n = A->n;
+    int32_t tmp[4096];
+    memset(target_out, 0, sizeof(int32_t) * S3);
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int r = 0; r < R; r++) {
+        int32_t f[3][64];
+        uint32_t blk[4] = {0, 0, 0, 0};
+        int az = 1; /* all groups of the current factor so far are zero */
+        for (int m = 0; m < 3 * A->ng; m++) {
+            if ((m & 7) == 0) {
+                uint32_t ctr[4] = {(uint32_t)d, (uint32_t)(d >> 32), (uint32_t)r, (uint32_t)(m >> 3)};
+                orc_philox4x32_10(ctr, key, blk);
+            }
+            const int fac = m / A->ng, g = m % A->ng;
+            if (g == 0) az = 1;
+            const uint32_t word = blk[(m >> 1) & 3], h = (m & 1) ? (word >> 16) : (word & 0xFFFFu);
+            const int size = (g < A->ng - 1) ? 3 : A->last;
+            const uint16_t b = A->tab[az ? 2 + g : (size == 3 ? 0 : 1)][h & 127];
+            const int o = ((h >> 7) < (uint32_t)(b & 511)) ? (int)(h & 127) : (int)(b >> 9);
+            if (size == 3) {
+                f[fac][3 * g] = values[o % n], f[fac][3 * g + 1] = values[(o / n) % n], f[fac][3 * g + 2] = values[o / (n * n)];
+                az = az && o == A->zo3;
+            } else {
+                f[fac][3 * g] = values[o];
+                az = az && o == A->zo1;
+            }
+        }
+        int32_t *tok = tokens_out + r * 3 * S;
+        for (int m = 0; m < 3; m++)
+            for (int i = 0; i < S; i++) tok[m * S + i] = f[m][i] + shift;
+        orc_uvw_to_tensor(f[0], f[1], f[2], S, tmp);
+        for (int e = 0; e < S3; e++) target_out[e] += tmp[e];
+    }
+}
+
+void orc_demos_philox_v2_batch(uint64_t seed, uint64_t d0, int64_t n, const int32_t *values, const double *probs, int n_values,
+                               int R, int S, int shift, int32_t *tokens_out, int32_t *targets_out) {
+    const int64_t S3 = (int64_t)S * S * S;
+    orc_alias A;
+    orc_alias_build(values, probs, n_values, S, &A);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++)
+        orc_demo_philox_v2(seed, d0 + (uint64_t)i, values, &A, R, S, shift, tokens_out + i * R * 3 * S, targets_out + i * S3);
+}
+
 /* Random unimodular triple (ours): M_f = L*U for f = 0,1,2 (A,B,C).  Entry
  * (r,c) of the draw grid uses byte (r*S+c)%16 (little-endian within the four
  * words) of Philox block (r*S+c)/16 with ctr = (block, f, 0x6D617473, d_lo)

@@ -184,9 +184,32 @@ def philox_thresholds(probs) -> np.ndarray:
     return thr
 
 
+def alias_applies(values, probs, S: int) -> bool:
+    """Contract v2 (group alias sampler) covers alphabets of at most five values with P(0) <= 0.999."""
+    v, p = _i32(values), np.ascontiguousarray(probs, dtype=np.float64)
+    return bool(lib().orc_alias_applies(_p(v), _p(p), C.c_int(len(v)), C.c_int(S)))
+
+
+def alias_tables(values, probs, S: int) -> np.ndarray:
+    """The alias tables of contract v2: uint16 (8, 128) -- [0] plain group of three, [1] plain single entry, [2 + g] tilted
+    table of group g."""
+    v, p = _i32(values), np.ascontiguousarray(probs, dtype=np.float64)
+    out = np.zeros((8, 128), dtype=np.uint16)
+    lib().orc_alias_tables(_p(v), _p(p), C.c_int(len(v)), C.c_int(S), _p(out))
+    return out
+
+
 def demos_philox(seed: int, d0: int, n: int, values, probs, R: int, S: int, shift: int, max_tries: int = 64):
-    """Throughput-mode contract (ours) -> (tokens (n,R,3S), targets (n,S,S,S), exhausted)."""
+    """Throughput-mode contracts (ours) -> (tokens (n,R,3S), targets (n,S,S,S), exhausted): v2 (group alias tables, no
+    rejection loop) where it applies, else v1 (thresholded 15-bit draws, bounded rejection loop)."""
     values = _i32(values)
+    if alias_applies(values, probs, S):
+        p64 = np.ascontiguousarray(probs, dtype=np.float64)
+        tokens = np.empty((n, R, 3 * S), dtype=np.int32)
+        targets = np.empty((n, S, S, S), dtype=np.int32)
+        lib().orc_demos_philox_v2_batch(C.c_uint64(seed), C.c_uint64(d0), C.c_int64(n), _p(values), _p(p64), C.c_int(len(values)),
+                                        C.c_int(R), C.c_int(S), C.c_int(shift), _p(tokens), _p(targets))
+        return tokens, targets, 0
     thr = philox_thresholds(probs)
     tokens = np.empty((n, R, 3 * S), dtype=np.int32)
     targets = np.empty((n, S, S, S), dtype=np.int32)

@@ -198,3 +198,59 @@ def test_misc_reference_helpers(golden):
     g = golden["misc"]
     assert g["scalars_b"].shape == (5, 1) and (g["scalars_b"] == 3).all() and g["scalars_s"].tolist() == [3.0]
     assert str(g["str_key"]) == "1_-2_0_3"
+
+
+def test_alias_sampler_contract_v2():
+    """Throughput-mode contract v2 (group alias tables): the library's host-side table builder and the oracle's
+    restatement agree bit for bit; the tables encode the reference's distribution (i.i.d. entries, factor conditioned on
+    being non-zero, utils.py:222-232); the sampled demos follow it."""
+    import ctypes as C
+    import itertools
+
+    from mat_mul_b200 import _lib
+
+    L = _lib.lib()
+    cases = [((-1, 0, 1), (0.15, 0.7, 0.15)), ((-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05)), ((-2, -1, 0, 1, 2), (0.2,) * 5),
+             ((-1, 0, 1), (0.1, 0.8, 0.1)), ((1, 2), (0.3, 0.7)), ((-2, -1, 0, 1, 2), (1.0, 2.0, 3.0, 2.0, 1.0))]
+    for values, probs in cases:
+        for S in (4, 9, 16):
+            assert orc.alias_applies(values, probs, S)
+            want = orc.alias_tables(values, probs, S)
+            got = np.zeros((8, 128), dtype=np.uint16)
+            v = np.array(values, dtype=np.int8)
+            p = np.array(probs, dtype=np.float64)
+            assert L.tg_demo_alias_tables(v.ctypes.data, p.ctypes.data, len(v), S, got.ctypes.data) == 0
+            assert np.array_equal(got, want), (values, probs, S)
+            # the distribution a table encodes: P(outcome) = (sum over buckets of thr / 512 for own + (1 - thr / 512) for alias) / 128
+            n, pn = len(values), np.array(probs, dtype=np.float64) / np.sum(probs)
+            def table_dist(t):
+                d = np.zeros(128)
+                for o in range(128):
+                    thr, al = int(t[o]) & 511, int(t[o]) >> 9
+                    q = 1.0 if (thr == 511 and al == o) else thr / 512.0
+                    d[o] += q / 128
+                    d[al] += (1 - q) / 128
+                return d
+            p3 = np.array([pn[o % n] * pn[(o // n) % n] * pn[o // (n * n)] for o in range(n ** 3)])
+            assert np.abs(table_dist(want[0])[: n ** 3] - p3).max() < 2.0 ** -13  # 9-bit thresholds per bucket: outcome probabilities to ~2^-13 absolute
+            assert np.abs(table_dist(want[1])[:n] - pn).max() < 2.0 ** -13
+            if 0 in values:  # the last group's tilted table never yields the zero outcome: a factor cannot end all zero
+                ng, z = (S + 2) // 3, values.index(0)
+                last_zero = z if S - 3 * (ng - 1) == 1 else z * (1 + n + n * n)
+                assert table_dist(want[2 + ng - 1])[last_zero] == 0.0
+    assert not orc.alias_applies((-1, 0, 1), (0.0, 1.0, 0.0), 4) and not orc.alias_applies(tuple(range(-3, 3)), (1,) * 6, 9)
+    # sampled factors: never all zero, entry frequencies = the conditional distribution of the reference's accepted factors
+    values, probs, S, R, N = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05), 4, 7, 6000
+    tok, tgt, ex = orc.demos_philox(1, 0, N, values, probs, R, S, 2)
+    fac = tok.reshape(N * R * 3, S) - 2
+    assert ex == 0 and fac.any(axis=1).all()
+    pn = np.array(probs)
+    exact = {}
+    for combo in itertools.product(range(5), repeat=S):
+        if any(values[c] != 0 for c in combo):
+            exact[combo] = np.prod(pn[list(combo)])
+    zsum = sum(exact.values())
+    p_entry0_zero = sum(v for c, v in exact.items() if values[c[0]] == 0) / zsum  # P(first entry = 0 | factor non-zero)
+    assert abs((fac[:, 0] == 0).mean() - p_entry0_zero) < 0.006 and abs((fac[:, 3] == 0).mean() - p_entry0_zero) < 0.006
+    assert abs((fac == 2).mean() - (fac == -2).mean()) < 0.004
+    assert np.array_equal(tgt[5], sum(orc.uvw_to_tensor(*(tok[5, r].reshape(3, S) - 2)) for r in range(R)))
