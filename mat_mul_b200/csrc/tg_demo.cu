@@ -123,25 +123,38 @@ __device__ __forceinline__ void draw_triple_alias(uint32_t words[(3 * S + 3) / 4
     }
 #pragma unroll
     for (int w = 0; w < NW; w++) words[w] = 0;
+    // both candidate buckets of every group first (the tilted table of its position and the plain table): their loads do
+    // not depend on each other, only the choice between them follows the factor's "all zero so far" chain
+    uint32_t h[A::ND], bt[A::ND], bp[A::ND];
+#pragma unroll
+    for (int m = 0; m < A::ND; m++) {
+        const int g = m % A::NG;
+        const bool three = g < A::NG - 1 || A::LAST == 3;
+        h[m] = (m & 1) ? (blk[m >> 1] >> 16) : (blk[m >> 1] & 0xFFFFu);
+        bt[m] = s_tab[g * ALIAS_BUCKETS + (h[m] & 127u)];
+        bp[m] = g == 0 ? 0u : s_tab[(three ? A::NG : A::NG + 1) * ALIAS_BUCKETS + (h[m] & 127u)];
+    }
+    uint32_t o[A::ND];
 #pragma unroll
     for (int f = 0; f < 3; f++) {
         bool az = true; // every group of this factor so far is all zero
 #pragma unroll
         for (int g = 0; g < A::NG; g++) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int m = f * A::NG + g;
-            const uint32_t h = (m & 1) ? (blk[m >> 1] >> 16) : (blk[m >> 1] & 0xFFFFu);
             const bool three = g < A::NG - 1 || A::LAST == 3;
-            const int plain = three ? A::NG : A::NG + 1;
-            const uint32_t bucket = s_tab[(az ? g : plain) * ALIAS_BUCKETS + (h & 127u)];
-            const uint32_t o = ((h >> 7) < (bucket & 511u)) ? (h & 127u) : (bucket >> 9);
-            const uint32_t tk = three ? s_lut3[o] : s_lut1[o];
-            az = az && (o == (three ? ap.zo3 : ap.zo1));
-            const int B = f * S + 3 * g; // byte offset of the group in the record
-            words[B >> 2] |= tk << (8 * (B & 3));
-            if ((B & 3) + (three ? 3 : 1) > 4) words[(B >> 2) + 1] |= tk >> (32 - 8 * (B & 3));
+            const uint32_t bucket = (g == 0 || az) ? bt[m] : bp[m];
+            o[m] = ((h[m] >> 7) < (bucket & 511u)) ? (h[m] & 127u) : (bucket >> 9);
+            az = az && (o[m] == (three ? ap.zo3 : ap.zo1));
         }
+    }
+#pragma unroll
+    for (int m = 0; m < A::ND; m++) {
+        const int f = m / A::NG, g = m % A::NG;
+        const bool three = g < A::NG - 1 || A::LAST == 3;
+        const uint32_t tk = three ? s_lut3[o[m]] : s_lut1[o[m]];
+        const int B = f * S + 3 * g; // byte offset of the group in the record
+        words[B >> 2] |= tk << (8 * (B & 3));
+        if ((B & 3) + (three ? 3 : 1) > 4) words[(B >> 2) + 1] |= tk >> (32 - 8 * (B & 3));
     }
 }
 
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (MMA == 0 ? C::main_bytes(R) : MMA > 0 ? C::rec_region(R) + MMA_SCRATCH : 0)); // [TG]
     uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
     uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16); ALIAS: the tables live here instead
-    uint32_t *s_alias = s_list;
+    uint32_t *s_alias = MMA > 0 ? reinterpret_cast<uint32_t *>(smem + C::rec_region(R)) : s_list; // fused kernels: the (not yet used) MMA scratch
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -489,15 +502,16 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
         const uint8_t *rec0 = s_rec + (size_t)g * R * C::REC;
         const int voff = 4 * KW + S + j; // byte offset of v_j in the record
         // one term: acc[i][.] += u_i * (v_j * pack(w))
-        auto term = [&](int r) {
+        auto load_rec = [&](int r, uint32_t (&q)[C::REC / 4], int &vj) {
             const uint8_t *rec = rec0 + (size_t)r * C::REC;
-            uint32_t q[C::REC / 4];
 #pragma unroll
             for (int m = 0; m < C::REC / 16; m++) {
                 const uint4 v4 = reinterpret_cast<const uint4 *>(rec)[m];
                 q[4 * m] = v4.x, q[4 * m + 1] = v4.y, q[4 * m + 2] = v4.z, q[4 * m + 3] = v4.w;
             }
-            const int vj = (int)reinterpret_cast<const int8_t *>(rec)[voff];
+            vj = (int)reinterpret_cast<const int8_t *>(rec)[voff];
+        };
+        auto apply_rec = [&](const uint32_t (&q)[C::REC / 4], int vj) {
             if constexpr (GUARD) bound += abs(vj);
             int32_t vw[KW];
 #pragma unroll
@@ -518,19 +532,27 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
         if (cat.sparse_terms && R <= 32) {
             // most coefficients are zero (P(0) = 0.7 in the reference's distributions): a term with v_j = 0 adds nothing to
             // this thread's entries, so every lane walks only ITS non-zero terms (a bit mask over r, built from the v_j
-            // bytes of the records); the warp runs max-over-lanes iterations (~12 of 23) instead of R
+            // bytes of the records); the warp runs max-over-lanes iterations (~12 of 23) instead of R.  (Loading the record of
+            // the next term before applying the current one was measured: 0.792 vs 0.772 ms per 2^20 demos -- not kept.)
             uint32_t tmask = 0, bit = 1;
 #pragma unroll 4
             for (int r = 0; r < R; r++, bit <<= 1)
                 if (reinterpret_cast<const int8_t *>(rec0 + (size_t)r * C::REC)[voff] != 0) tmask |= bit;
             while (tmask) {
-                const int r = __ffs((int)tmask) - 1;
+                uint32_t q[C::REC / 4];
+                int vj;
+                load_rec(__ffs((int)tmask) - 1, q, vj);
                 tmask &= tmask - 1;
-                term(r);
+                apply_rec(q, vj);
             }
         } else {
 #pragma unroll 2
-            for (int r = 0; r < R; r++) term(r);
+            for (int r = 0; r < R; r++) {
+                uint32_t q[C::REC / 4];
+                int vj;
+                load_rec(r, q, vj);
+                apply_rec(q, vj);
+            }
         }
         if (GUARD && bound * shift * shift > 191) {
             // a final entry might alias inside the packed words: recompute this thread's entries one by one
@@ -682,7 +704,8 @@ template <int S, int NT, int NPASS, int MMA>
 static int launch_demo_alias(unsigned long long first, long long N, int R, int shift, const Categorical &cat, const AliasParams &ap,
                              uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     using C = DemoCfg<S, NT, NPASS>;
-    constexpr int TAIL = (2 * NT * 4 > AliasGeo<S>::SMEM_BYTES ? 2 * NT * 4 : AliasGeo<S>::SMEM_BYTES);
+    constexpr int TAIL = MMA > 0 ? 2 * NT * 4 : (2 * NT * 4 > AliasGeo<S>::SMEM_BYTES ? 2 * NT * 4 : AliasGeo<S>::SMEM_BYTES);
+    static_assert(MMA <= 0 || AliasGeo<S>::SMEM_BYTES <= acc16::WARP_WORDS * 4, "the alias tables overlay one warp's MMA scratch");
     const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : C::main_bytes(R)) + C::TG * 4 + 16 + TAIL;
     if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
@@ -709,7 +732,18 @@ static int dispatch_demo_alias(unsigned long long first, long long N, int R, int
         if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
             return launch_demo_alias<4, 256, 4, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
         return launch_demo_alias<4, 256, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
-    case 9: return launch_demo_alias<9, 128, 2, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+    case 9:
+#ifdef TG_TUNING
+        switch (tuning_env("TG_DEMO_VARIANT", 0)) {
+        case 1: return launch_demo_alias<9, 256, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        case 2: return launch_demo_alias<9, 128, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        case 3: return launch_demo_alias<9, 256, 2, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        case 4: return launch_demo_alias<9, 64, 2, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        case 5: return launch_demo_alias<9, 64, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
+        default: break;
+        }
+#endif
+        return launch_demo_alias<9, 128, 2, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
     case 16:
         if (demo_acc16_mma_applies(R)) {
             if (R <= 32) return launch_demo_alias<16, 128, 2, 2>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
