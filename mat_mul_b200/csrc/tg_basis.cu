@@ -746,9 +746,12 @@ static int change_of_basis_impl(const int8_t *slab_in, const int8_t *mats, int p
         if (flags && variant != 1) {
             const int rc = tg::launch_basis_mma9(slab_in, mats, ms, slab_out, out16, flags, N, st);
             if (rc != TG_OK) return rc;
-        } else if (flags) {
+        }
+#ifdef TG_TUNING
+        else if (flags) { // the packed-lane kernel (3 x 10-bit lanes): A/B timing only
             if (out16) TG_BASIS_FAST(9, true) else TG_BASIS_FAST(9, false)
         }
+#endif
         if (out16) { TG_BASIS_EXACT(9, true) } else { TG_BASIS_EXACT(9, false) }
         break;
     case 16:

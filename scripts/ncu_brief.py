@@ -7,6 +7,7 @@ out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], captu
 units = float(sys.argv[2]) if len(sys.argv) > 2 else None
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[0]
+units_row = dict(zip(hdr, rows[1]))  # ncu prints each raw metric in a unit of its own choosing
 K = {
     "time_us": "gpu__time_duration.sum", "cycles": "sm__cycles_elapsed.max", "warp_inst": "smsp__inst_executed.sum",
     "thread_inst": "thread_inst_executed", "issue_active%": "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -27,7 +28,8 @@ for r in rows[2:]:
     line = []
     for k, m in K.items():
         if m in d and d[m] not in ("", "no data"):
-            line.append(f"{k}={float(d[m].replace(',', '')):.4g}")
+            u = units_row.get(m, "") if k.startswith("dram_") or k == "time_us" else ""
+            line.append(f"{k.replace('_MB', '')}={float(d[m].replace(',', '')):.4g}{('[' + u + ']') if u else ''}")
     print("  " + "  ".join(line))
     if units:
         cyc = float(d["sm__cycles_elapsed.max"].replace(",", ""))

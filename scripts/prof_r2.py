@@ -1,4 +1,4 @@
-"""One launch set of a round-2 kernel at bench size (for ncu): python scripts/prof_r2.py sample|basis9|basis16|basis4|demo9|demo4"""
+"""One launch set of a round-2 kernel at bench size (for ncu): python scripts/prof_r2.py sample|basis9|basis16|basis4|demo9|demo4|demo16|step|rollout|rank|expand"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -30,5 +30,24 @@ elif which.startswith("demo"):
     slab = torch.empty((N, lay.game_pitch), dtype=torch.int8, device="cuda")
     for _ in range(3):
         env.make_synthetic_demos(N, R, S, vals, probs, shift, seed=1, tape=tape, slab=slab)
+elif which in ("step", "rollout", "rank", "expand"):
+    S, R, N = 9, 23, 1 << 20
+    tape, slab, _ = env.make_synthetic_demos(N, R, S, V5, P5, 2, seed=1)
+    out = torch.empty_like(slab)
+    if which == "step":
+        fl, nz = torch.empty(N, dtype=torch.uint8, device="cuda"), torch.empty(N, dtype=torch.int32, device="cuda")
+        for r in range(3):
+            env.step_batch(slab, tape[R - 1 - r], S, 2, out=out, flags=fl, nnz=nz)
+    elif which == "rollout":
+        rev = tape.flip(0).contiguous()
+        for _ in range(3):
+            env.rollout(slab, rev, S, 2, out=out)
+    elif which == "rank":
+        for _ in range(3):
+            env.slice_rank(slab[: 1 << 17], S)
+    else:
+        tb = tape[:8, : 1 << 17].permute(1, 0, 2).contiguous()
+        for _ in range(3):
+            env.expand_children(slab[: 1 << 17], tb, S, 2)
 torch.cuda.synchronize()
 print("ok")
