@@ -378,7 +378,7 @@ def measure_demos(env, torch, dist, dev, S, B, R, values, probs, shift, world, r
         gen(Ke - 1)
         same = bool(torch.equal(h_slab[:4096], slab[:4096].cpu()) and torch.equal(h_tape[:, :4096], tape[:, :4096].cpu()))
         out["e2e"] = {"value": world * B / dt, "unit": "demos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h, "steps": Ke,
-                      "api": "tg_demo_gen_host (C ABI, pinned host buffers, 64Ki-demo chunks over 3 streams)",
+                      "api": "tg_demo_gen_host (C ABI, pinned host buffers, 64Ki-demo chunks through dedicated kernel / D2H streams chained by events)",
                       "ceiling_gbs": d2h / ceil_s / 1e9, "frac_of_ceiling": (d2h / dt) / (d2h / ceil_s), "host_equals_device": same}
         del h_tape, h_slab
     if with_cpu and world == 1:
@@ -439,7 +439,7 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
     out["change_of_basis"], _ = basis_block(S, slab, nb, 0.3)
     idx = torch.randint(0, B * R, (1 << 16,), device=dev)
     store = env.DemoStore.from_tape(tape3, slab, S, shift)  # demo-major action records next to the step-major tape
-    ms = _time_ms(lambda: store.samples(idx, 2, replay_shift=shift), 3, torch)
+    ms = _time_ms(lambda: store.samples(idx, 2, replay_shift=shift), 10, torch)
     out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2,
                           "hbm_frac": idx.numel() * (2 * S ** 3 * 4) / (ms * 1e-3) / 1e9 / peak}
     del store
@@ -684,7 +684,7 @@ def main() -> None:
         barrier()
         ceil_s = max_over_ranks(copy_ceiling(torch, dev, h2d, d2h, Be >> 16, 3), torch, dist, dev, world)
         e2e = {"value": world * Be * Ke / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-               "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks over 3 streams)",
+               "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks through dedicated H2D / kernel / D2H streams chained by events)",
                "host_cores_bound": len(numa_cores),
                "ceiling_gbs": (h2d + d2h) / ceil_s / 1e9, "achieved_gbs": (h2d + d2h) * Ke / dt / 1e9,
                "frac_of_ceiling": ((h2d + d2h) * Ke / dt) / ((h2d + d2h) / ceil_s),

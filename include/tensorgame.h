@@ -252,11 +252,12 @@ int tg_sample_unimodular(uint64_t seed, uint64_t first, int64_t N, int S, double
 
 /* ---- host-buffer path (end-to-end through PCIe) -------------------------- */
 typedef struct tg_host_ctx tg_host_ctx;
-/* creates streams and device staging for chunks of up to max_chunk games */
+/* creates three streams, events and four device staging buffers for chunks of up to max_chunk games */
 int tg_host_ctx_create(tg_host_ctx **ctx, int device, int S, int64_t max_chunk);
 int tg_host_ctx_destroy(tg_host_ctx *ctx);
-/* same contract as tg_step with HOST slabs/tapes/flags/nnz; chunks are
- * pipelined H2D -> kernel -> D2H over three streams; returns when done. */
+/* same contract as tg_step with HOST slabs/tapes/flags/nnz; chunks flow
+ * through dedicated H2D / kernel / D2H streams chained by events per staging
+ * buffer (both copy engines stream back to back); returns when done. */
 int tg_step_host(tg_host_ctx *ctx, const int8_t *slab_in, const uint8_t *tape, int8_t *slab_out, uint8_t *flags,
                  int32_t *nnz, int64_t B, int shift);
 /* tg_rollout with HOST buffers: the slab crosses PCIe once per K steps instead of once per step -- the case where the
