@@ -293,9 +293,11 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ e2e helpers
-def copy_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, chunks: int, reps: int) -> float:
+def copy_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, chunks: int, reps: int, barrier=None) -> float:
     """Raw bidirectional pinned-copy ceiling of this host<->GPU path: the bytes one e2e step moves, as plain async
-    copies in the same chunking on two streams (H2D and D2H concurrently), no kernel.  Returns seconds per step."""
+    copies in the same chunking on two streams (H2D and D2H concurrently), no kernel.  Returns seconds per step.
+    `barrier` is called after the buffers exist and the copies are warm, so that at N > 1 every rank's timed copies
+    run while all the others' do (allocation / pinning takes a different time on every rank)."""
     hin = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
     hout = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
     din = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
@@ -312,6 +314,8 @@ def copy_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, chunks: int, reps: 
 
     one()
     torch.cuda.synchronize()
+    if barrier is not None:
+        barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
         one()
@@ -373,7 +377,7 @@ def measure_demos(env, torch, dist, dev, S, B, R, values, probs, shift, world, r
         dt = max_over_ranks((time.perf_counter() - t0) / Ke, torch, dist, dev, world)
         hs.close()
         d2h = B * (lay.game_pitch + R * lay.token_pitch + 1)
-        ceil_s = max_over_ranks(copy_ceiling(torch, dev, 16, d2h, 16, 3), torch, dist, dev, world)
+        ceil_s = max_over_ranks(copy_ceiling(torch, dev, 16, d2h, 16, Ke, barrier), torch, dist, dev, world)
         # the host copy equals the device result of the same seed (checked on a slice, outside the timed region)
         gen(Ke - 1)
         same = bool(torch.equal(h_slab[:4096], slab[:4096].cpu()) and torch.equal(h_tape[:, :4096], tape[:, :4096].cpu()))
@@ -682,14 +686,14 @@ def main() -> None:
         dt = max_over_ranks(time.perf_counter() - t0, torch, dist, dev, world)
         h2d, d2h = Be * (lay.game_pitch + lay.token_pitch), Be * (lay.game_pitch + 5)
         barrier()
-        ceil_s = max_over_ranks(copy_ceiling(torch, dev, h2d, d2h, Be >> 16, 3), torch, dist, dev, world)
+        ceil_s = max_over_ranks(copy_ceiling(torch, dev, h2d, d2h, Be >> 16, Ke, barrier), torch, dist, dev, world)
         e2e = {"value": world * Be * Ke / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                "api": "tg_step_host (C ABI, pinned host buffers, 64Ki-game chunks through dedicated H2D / kernel / D2H streams chained by events)",
                "host_cores_bound": len(numa_cores),
                "ceiling_gbs": (h2d + d2h) / ceil_s / 1e9, "achieved_gbs": (h2d + d2h) * Ke / dt / 1e9,
                "frac_of_ceiling": ((h2d + d2h) * Ke / dt) / ((h2d + d2h) / ceil_s),
                "ceiling": "the same bytes per step as plain pinned cudaMemcpyAsync in the same chunks, H2D and D2H streams "
-                          "concurrently, no kernel, all ranks at once (max over ranks)"}
+                          "concurrently, no kernel, as many repetitions as e2e steps, all ranks at once behind a barrier (max over ranks)"}
         # the K-step host entry (the _take_actions use case, datasets.py:144-153): the slab crosses PCIe once per R steps
         h_tapeK = torch.empty((R, Be, lay.token_pitch), dtype=torch.uint8).pin_memory()
         h_tapeK.copy_(tape3.flip(0))
