@@ -221,7 +221,11 @@ int tg_slice_rank(const int8_t *slab, int32_t *ranks, int64_t B, int S, void *st
 /* ---- K7: state keys ------------------------------------------------------- */
 /* 64-bit key per head tensor, replacing the string keys of utils.py:164-169
  * used by the MCTS tree (act.py:37,93,146,171,189,192,210): equal states <=>
- * equal keys (up to a 2^-64 collision); the all-zero state has key 0. */
+ * equal keys (up to a ~2^-60 collision); the all-zero state has key 0.
+ * key(T) = sum_{i,j,k} T[i][j][k] * A_i * B_j * C_k  (mod 2^64) with A_i = splitmix64(0x1000 + i) | 1,
+ * B_j = splitmix64(0x2000 + j) | 1, C_k = splitmix64(0x3000 + k) | 1 -- the trilinear form of the state at three fixed
+ * odd vectors: linear in T, and the key of a rank-1 action u (x) v (x) w is (sum u_i A_i)(sum v_j B_j)(sum w_k C_k),
+ * which is how tg_expand_children keys a child without a pass over it.  (TG_VERSION 200 changed the constants.) */
 int tg_state_key(const int8_t *slab, uint64_t *keys, int64_t B, int S, void *stream);
 
 /* ---- K5: change-of-basis augmentation ------------------------------------- */

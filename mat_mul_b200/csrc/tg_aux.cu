@@ -807,8 +807,10 @@ __global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__re
 
 // ------------------------------------------------------------------ K7
 // 64-bit state key replacing the string key of utils.py:164-169 (dict key of
-// the MCTS tree, act.py:37...210): a linear hash, sum over entries e of value * C_e,
-// C_e = splitmix64(e+1) | 1, e the dense index (i*S+j)*S+k.
+// the MCTS tree, act.py:37...210): a linear hash, sum over entries of value * A_i * B_j * C_k (the trilinear form of
+// the state at three fixed odd 64-bit vectors, A_i = splitmix64(0x1000 + i) | 1, B_j = splitmix64(0x2000 + j) | 1,
+// C_k = splitmix64(0x3000 + k) | 1).  The product structure is what lets tg_expand_children (tg_expand.cu) get a
+// child's key from its action's 3 S tokens alone.
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -816,40 +818,70 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
     return z ^ (z >> 31);
 }
 
-// key(T) = sum_e T[e] * C_e (mod 2^64), C_e = splitmix64(e + 1) | 1: one 64-bit multiply-add per non-zero entry, the
-// constants in a shared-memory table built at kernel start; per-game sums through shared memory, one store per game.
+__device__ __forceinline__ unsigned long long key_const(unsigned base, int i) { return splitmix64((unsigned long long)(base + i)) | 1ull; }
+
+// key(T) = sum T[i][j][k] * A_i * B_j * C_k (mod 2^64).  One thread per word column of a game: its four entries of row i
+// as unsigned offset-binary bytes (entry + 128) times the compile-time A_i go into four 64-bit accumulators (one wide
+// and one 32-bit multiply-add per entry; the offset's share -128 sum_i A_i is their start value), which then meet the
+// column's four B_j C_k (registers).  The WR partial sums of a game meet in shared memory -- no atomics, no table.
 template <int S>
 __global__ void __launch_bounds__(256) state_key_kernel(const int8_t *__restrict__ slab, unsigned long long *__restrict__ keys,
                                                         long long B) {
     using G = Geo<S>;
     constexpr int TG = 256 / G::WR; // games per pass of the CTA
-    __shared__ unsigned long long s_c[S * G::RP]; // C by slab offset (i, 4c+q); 0 in the row padding
-    __shared__ unsigned long long s_key[TG];
+    __shared__ unsigned long long s_ph[256];
     const int tid = threadIdx.x;
-    for (int x = tid; x < S * G::RP; x += 256) {
-        const int i = x / G::RP, jk = x % G::RP;
-        s_c[x] = jk < G::S2 ? (splitmix64((unsigned long long)(i * G::S2 + jk + 1)) | 1ull) : 0ull;
-    }
     const int gl = tid / G::WR, c = tid % G::WR;
-    for (long long g0 = (long long)blockIdx.x * TG; g0 < B; g0 += (long long)gridDim.x * TG) {
-        if (tid < TG) s_key[tid] = 0;
-        __syncthreads();
+    unsigned long long kb[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int jk = 4 * c + q;
+        kb[q] = jk < G::S2 ? key_const(0x2000, jk / S) * key_const(0x3000, jk % S) : 0ull;
+    }
+    unsigned long long a0 = 0;
+#pragma unroll
+    for (int i = 0; i < S; i++) a0 -= 128ull * key_const(0x1000, i);
+    uint32_t w[S];
+    auto fetch = [&](long long g0) { // this thread's word column of its game of the pass starting at g0 (zero state beyond B)
         const long long g = g0 + gl;
         if (gl < TG && g < B) {
-            unsigned long long h = 0;
             const uint32_t *col = reinterpret_cast<const uint32_t *>(slab + g * G::GP) + c;
 #pragma unroll
-            for (int i = 0; i < S; i++) {
-                const uint32_t w = col[i * G::WR];
-                if (w == 0) continue;
+            for (int i = 0; i < S; i++) w[i] = __ldg(col + i * G::WR) ^ 0x80808080u;
+        } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    h += (unsigned long long)(long long)(int8_t)((w >> (8 * q)) & 0xFFu) * s_c[i * G::RP + 4 * c + q];
-            }
-            if (h) atomicAdd(&s_key[gl], h);
+            for (int i = 0; i < S; i++) w[i] = 0x80808080u;
         }
+    };
+    fetch((long long)blockIdx.x * TG);
+    for (long long g0 = (long long)blockIdx.x * TG; g0 < B; g0 += (long long)gridDim.x * TG) {
+        unsigned long long acc[4] = {a0, a0, a0, a0};
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[q] += (unsigned long long)((w[i] >> (8 * q)) & 0xFFu) * key_const(0x1000, i);
+        }
+        const unsigned long long h = acc[0] * kb[0] + acc[1] * kb[1] + acc[2] * kb[2] + acc[3] * kb[3];
+        fetch(g0 + (long long)gridDim.x * TG); // the next pass's loads fly over this pass's reduction
+        s_ph[tid] = h;
         __syncthreads();
-        if (tid < TG && g0 + tid < B) keys[g0 + tid] = s_key[tid];
+        if constexpr (G::WR <= 32) {
+            if (tid < TG && g0 + tid < B) {
+                unsigned long long k = 0;
+#pragma unroll
+                for (int x = 0; x < G::WR; x++) k += s_ph[tid * G::WR + x];
+                keys[g0 + tid] = k;
+            }
+        } else { // S = 16: 64 partial sums per game, one warp per game
+            static_assert(G::WR <= 32 || (G::WR == 64 && TG <= 8), "warp-per-game reduction");
+            const int wp = tid >> 5, ln = tid & 31;
+            if (wp < TG && g0 + wp < B) {
+                unsigned long long k = s_ph[wp * 64 + ln] + s_ph[wp * 64 + 32 + ln];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
+                if (ln == 0) keys[g0 + wp] = k;
+            }
+        }
         __syncthreads();
     }
 }

@@ -491,11 +491,12 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     for (int pass = 0; pass < NPASS; pass++) {
     const int g = pass * C::GPASS + tid / S;
     const bool worker = tid < C::ACTIVE && g < ng;
+    // the sums start at 128 per byte: integer form + H4 = offset-binary bytes, which is what the end of the pass wants
     int32_t acc[S][KW];
 #pragma unroll
     for (int i = 0; i < S; i++)
 #pragma unroll
-        for (int m = 0; m < KW; m++) acc[i][m] = 0;
+        for (int m = 0; m < KW; m++) acc[i][m] = (int32_t)H4;
     uint32_t bad = 0;
     if (worker) {
         int bound = 0;
@@ -579,14 +580,18 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                     acc[i][m] = (int32_t)word;
                 }
         } else {
+            // offset-binary byte b holds entry + 128: in [-64, 63] <=> bits 7 and 6 differ (padding bytes hold 128: fine);
+            // one LOP3 per word keeps the AND of (bit 7 ^ bit 6) over all bytes, another turns the word into two's complement
+            uint32_t ok = H4;
 #pragma unroll
             for (int i = 0; i < S; i++)
 #pragma unroll
                 for (int m = 0; m < KW; m++) {
-                    const uint32_t t = ((uint32_t)acc[i][m] + H4) ^ H4; // integer form -> two's complement bytes
-                    bad |= (t ^ (t << 1)) & ((m == KW - 1) ? (WLAST & H4) : H4);
-                    acc[i][m] = (int32_t)t;
+                    const uint32_t o = (uint32_t)acc[i][m];
+                    ok &= o ^ (o << 1);
+                    acc[i][m] = (int32_t)(o ^ H4);
                 }
+            bad = ~ok & H4;
         }
     }
     if constexpr (C::OVERLAY) __syncthreads(); // every record has been consumed: the slab tile takes over the same bytes

@@ -11,9 +11,10 @@
 // The parent is read ONCE: thread (parent, word column) keeps its S row words in registers and produces the k
 // children one after the other into a two-stage shared-memory tile; each child game leaves with a TMA bulk store
 // while the next one is computed.  HBM traffic per child: GP * (1 + 1/k) + TP + 13 bytes.
-// The state key is linear (sum_e T[e] * C_e mod 2^64, tg_state_key), so a child's key is the parent's key (hashed
-// once per parent) minus sum_e (u_i v_j w_k) * C_e over the few entries its rank-1 action changes -- not a second
-// pass over the child.  The constants C_e of a thread's word column live in a shared-memory table.
+// The state key is the trilinear form of the state at three fixed 64-bit vectors (sum T[i][j][k] A_i B_j C_k mod 2^64,
+// tg_state_key), so a child's key is the parent's key (hashed once per parent) minus
+// (sum u_i A_i)(sum v_j B_j)(sum w_k C_k): 3 S multiply-adds on the action's tokens, done for all TG * k children of the
+// block before the child loop -- no pass over the child, no per-entry work.
 #include "tg_step.cuh"
 
 namespace tg {
@@ -26,9 +27,8 @@ struct ExpCfg {
     static constexpr int STAGE_BYTES = TG * G::GP;
     static __host__ __device__ constexpr int tok_bytes(int k) { return (TG * k * G::TP + 15) & ~15; }
     // tokens, 2 child stages, per-(stage, game) partial word and key
-    static constexpr int CTAB_BYTES = S * G::RP * 8; // key constants by slab offset
     static __host__ __device__ constexpr int smem_bytes(int k) {
-        return tok_bytes(k) + 2 * STAGE_BYTES + 2 * TG * 4 + 3 * TG * 8 + 16 + CTAB_BYTES;
+        return tok_bytes(k) + 2 * STAGE_BYTES + 2 * TG * 4 + TG * 8 + 16 + NT * 8;
     }
 };
 
@@ -38,6 +38,8 @@ __device__ __forceinline__ unsigned long long splitmix64_e(unsigned long long z)
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
+// A_i / B_j / C_k of the state key (tg_state_key): base 0x1000 / 0x2000 / 0x3000
+__device__ __forceinline__ unsigned long long key_const(unsigned base, int i) { return splitmix64_e((unsigned long long)(base + i)) | 1ull; }
 
 template <int S, int NT, bool KEYS>
 __global__ void __launch_bounds__(NT)
@@ -50,10 +52,9 @@ __global__ void __launch_bounds__(NT)
     uint8_t *s_tok = smem;                                                            // [TG][k][TP]
     uint8_t *s_out = smem + C::tok_bytes(k);                                          // [2][TG][GP]
     uint32_t *s_part = reinterpret_cast<uint32_t *>(s_out + 2 * C::STAGE_BYTES);      // [2][TG]
-    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_part + 2 * C::TG); // [2][TG] key deltas, [TG] parent keys
-    unsigned long long *s_pkey = s_key + 2 * C::TG;
+    unsigned long long *s_pkey = reinterpret_cast<unsigned long long *>(s_part + 2 * C::TG); // [TG] parent keys
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_pkey + C::TG);
-    unsigned long long *s_c = reinterpret_cast<unsigned long long *>(s_bar + 2); // [S][RP]
+    unsigned long long *s_ph = reinterpret_cast<unsigned long long *>(s_bar + 2); // [NT] parent key, per word column
 
     const int tid = threadIdx.x;
     const long long g0 = (long long)blockIdx.x * C::TG;
@@ -69,13 +70,16 @@ __global__ void __launch_bounds__(NT)
     }
     // game padding of both child stages is zero and stays zero (threads only write their word columns of the S rows)
     for (int w = tid; w < 2 * C::STAGE_BYTES / 4; w += NT) reinterpret_cast<uint32_t *>(s_out)[w] = 0;
-    for (int i = tid; i < 2 * C::TG; i += NT) s_part[i] = 0, s_key[i] = 0;
-    for (int i = tid; i < C::TG; i += NT) s_pkey[i] = 0;
-    if constexpr (KEYS)
-        for (int x = tid; x < S * G::RP; x += NT) {
-            const int i = x / G::RP, jk = x % G::RP;
-            s_c[x] = jk < G::S2 ? (splitmix64_e((unsigned long long)(i * G::S2 + jk + 1)) | 1ull) : 0ull;
+    for (int i = tid; i < 2 * C::TG; i += NT) s_part[i] = 0;
+    // key constants of this thread's word column: B_j C_k of its four entries (0 in the row padding)
+    unsigned long long kb[4] = {0, 0, 0, 0};
+    if constexpr (KEYS) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int jk = 4 * L.c + q;
+            kb[q] = jk < G::S2 ? key_const(0x2000, jk / S) * key_const(0x3000, jk % S) : 0ull;
         }
+    }
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(s_bar, (uint32_t)(ng * k * G::TP));
@@ -91,26 +95,45 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
         for (int i = 0; i < S; i++) row[i] = H4;
     }
-    // sum_q (signed byte q of word) * C[row i][4c + q]
-    auto word_key = [&](int i, uint32_t word) {
-        unsigned long long h = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            h += (unsigned long long)(long long)(int8_t)((word >> (8 * q)) & 0xFFu) * s_c[i * G::RP + 4 * L.c + q];
-        return h;
-    };
     if constexpr (KEYS) {
-        if (active) { // the parent's key, once
-            unsigned long long h = 0;
+        // the parent's key, once: this thread's word column gives sum_q (B C)[4c + q] * sum_i A_i T[i][4c + q]; the rows
+        // are offset-binary bytes (entry + 128, unsigned: one wide multiply-add and one 32-bit one per entry), the
+        // offset's share -128 sum_i A_i is the accumulators' start value
+        unsigned long long a0 = 0;
 #pragma unroll
-            for (int i = 0; i < S; i++) {
-                const uint32_t t = row[i] ^ H4;
-                if (t != 0) h += word_key(i, t);
-            }
-            if (h) atomicAdd(&s_pkey[g], h);
+        for (int i = 0; i < S; i++) a0 -= 128ull * key_const(0x1000, i);
+        unsigned long long acc[4] = {a0, a0, a0, a0};
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[q] += (unsigned long long)((row[i] >> (8 * q)) & 0xFFu) * key_const(0x1000, i);
         }
+        s_ph[tid] = acc[0] * kb[0] + acc[1] * kb[1] + acc[2] * kb[2] + acc[3] * kb[3];
     }
     mbar_wait(s_bar, 0);
+    if constexpr (KEYS) {
+        __syncthreads();
+        if (tid < ng) {
+            unsigned long long h = 0;
+            for (int c = 0; c < G::WR; c++) h += s_ph[tid * G::WR + c];
+            s_pkey[tid] = h;
+        }
+        __syncthreads();
+        // child key = parent key - key of its rank-1 action, the latter from the action's tokens alone; one coalesced
+        // store of the block's TG * k keys
+        for (int x = tid; x < ng * k; x += NT) {
+            const uint8_t *tok = s_tok + (size_t)x * G::TP;
+            unsigned long long f[3];
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                unsigned long long a = 0;
+#pragma unroll
+                for (int i = 0; i < S; i++) a += (unsigned long long)(long long)((int)tok[m * S + i] - shift) * key_const(0x1000 * (m + 1), i);
+                f[m] = a;
+            }
+            keys[g0 * k + x] = s_pkey[x / k] - f[0] * f[1] * f[2];
+        }
+    }
 
     for (int c = 0; c < k; c++) {
         const int st = c & 1;
@@ -122,10 +145,8 @@ __global__ void __launch_bounds__(NT)
             const uint4 ut = *reinterpret_cast<const uint4 *>(tok);
             const uint32_t uw[4] = {ut.x, ut.y, ut.z, ut.w};
             const uint32_t nvw = (uint32_t)(-vw);
-            const uint32_t vwb = ((uint32_t)(-vw) + H4) ^ H4; // -(v w) of the four entries as two's complement bytes
             uint32_t cnt = 0, rng = 0;
             int uany = 0;
-            unsigned long long h = 0;
             uint32_t *col = reinterpret_cast<uint32_t *>(stage + (size_t)g * G::GP) + L.c;
 #pragma unroll
             for (int i = 0; i < S; i++) {
@@ -135,15 +156,9 @@ __global__ void __launch_bounds__(NT)
                 cnt += ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & L.hv) >> 7;
                 rng |= t ^ (t << 1);
                 uany |= negu;
-                if constexpr (KEYS) {
-                    // the word changes by -u_i * (v w bytes): its key contribution changes by -u_i * word_key(vw bytes)
-                    if (negu != 0 && vw != 0) h += (unsigned long long)(long long)negu * word_key(i, vwb);
-                }
             }
             atomicAdd(&s_part[st * C::TG + g], make_partial(byte_sum(cnt), vw != 0 && uany != 0,
                                                             (rng & L.hv) != 0 || tokens_out_of_range<S>(tok, L, shift)));
-            if constexpr (KEYS)
-                if (h) atomicAdd(&s_key[st * C::TG + g], h);
         }
         fence_proxy_async();
         __syncthreads();
@@ -155,14 +170,10 @@ __global__ void __launch_bounds__(NT)
             flags[child] = (uint8_t)partial_flags(sum);
             nnz[child] = (int32_t)(sum & 0xFFFFu);
             s_part[st * C::TG + tid] = 0;
-            if constexpr (KEYS) {
-                keys[child] = s_pkey[tid] + s_key[st * C::TG + tid];
-                s_key[st * C::TG + tid] = 0;
-            }
             bulk_wait_read<1>(); // the store of child c-1 (other stage) has drained: safe to overwrite next iteration
         }
         // (the barrier at the end of the NEXT iteration's compute orders "stage drained" before its reuse at c+2;
-        //  the one here orders the reset of s_part / s_key before the next child's atomics)
+        //  the one here orders the reset of s_part before the next child's atomics)
         __syncthreads();
     }
     if (tid < ng) bulk_wait<0>();

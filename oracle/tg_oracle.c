@@ -855,14 +855,23 @@ static uint64_t splitmix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-/* key(T) = sum_e T[e] * C_e  (mod 2^64),  C_e = splitmix64(e + 1) | 1,  e the dense index (i*S+j)*S+k: a linear
- * (multiply-add) hash with one odd 64-bit constant per position.  Linear, so the key of a child state is the key of
- * its parent minus the contribution of the rank-1 action; the all-zero state has key 0. */
+/* key(T) = sum_{i,j,k} T[i][j][k] * A_i * B_j * C_k  (mod 2^64),  A_i = splitmix64(0x1000 + i) | 1,
+ * B_j = splitmix64(0x2000 + j) | 1,  C_k = splitmix64(0x3000 + k) | 1: the trilinear form of T at three fixed odd 64-bit
+ * vectors (distinct per mode, so transposed states get different keys).  Linear, so the key of a child state is the key
+ * of its parent minus the contribution of the rank-1 action -- which is just (sum u_i A_i)(sum v_j B_j)(sum w_k C_k).
+ * The all-zero state has key 0. */
 uint64_t orc_state_key(const int32_t *T, int S) {
-    const int S3 = S * S * S;
     uint64_t h = 0;
-    for (int e = 0; e < S3; e++)
-        if (T[e] != 0) h += (uint64_t)(int64_t)T[e] * (splitmix64((uint64_t)(e + 1)) | 1ull);
+    for (int i = 0; i < S; i++) {
+        const uint64_t a = splitmix64(0x1000ull + (uint64_t)i) | 1ull;
+        for (int j = 0; j < S; j++) {
+            const uint64_t ab = a * (splitmix64(0x2000ull + (uint64_t)j) | 1ull);
+            for (int k = 0; k < S; k++) {
+                const int32_t t = T[(i * S + j) * S + k];
+                if (t != 0) h += (uint64_t)(int64_t)t * (ab * (splitmix64(0x3000ull + (uint64_t)k) | 1ull));
+            }
+        }
+    }
     return h;
 }
 
