@@ -164,7 +164,7 @@ struct DemoCfg {
     static constexpr int GPASS = NT / S;        // demos per pass of phase B: S threads per demo (thread = factor index j)
     static constexpr int TG = GPASS * NPASS;    // demos per CTA: a bigger tile amortises the tail of the sampling phase
     static constexpr int ACTIVE = GPASS * S;
-    static constexpr bool OVERLAY = NPASS == 1; // the slab tile reuses the bytes of the accumulate records
+    static constexpr bool TILE = S != 4;         // 4x4x4 games leave straight from the registers: no slab tile
     static constexpr int KW = (S + 3) / 4;       // packed words per run of S entries (one (i, j), k = 0..S-1)
     static constexpr int NCW = (2 * S + 3) / 4;  // words holding the u and v coefficient bytes
     static constexpr int NW = (3 * S + 3) / 4;   // token words of one action
@@ -174,13 +174,32 @@ struct DemoCfg {
     // different banks (768 B and 64 B pitches are 0 mod 128 / alias every other demo); each game leaves with its
     // own bulk store
     static constexpr int PITCH = G::GP + (S == 9 ? 32 : (S == 4 ? 16 : 0));
-    static constexpr int SLAB_BYTES = TG * PITCH;
+    static constexpr int PASS_SLAB = TILE ? GPASS * PITCH : 0;
     static __host__ __device__ constexpr int rec_bytes(int R) { return R * TG * REC; }
-    // slab tile, records, per-demo flags, work counter + 2 retry-list counters, 2 retry lists of NT entries
-    static __host__ __device__ constexpr int rec_region(int R) { return (rec_bytes(R) + 15) & ~15; }
-    static __host__ __device__ constexpr int main_bytes(int R) {
-        return OVERLAY ? (((rec_bytes(R) > SLAB_BYTES ? rec_bytes(R) : SLAB_BYTES) + 15) & ~15) : rec_region(R) + SLAB_BYTES;
+    static __host__ __device__ constexpr int rec_region(int R) { return (rec_bytes(R) + 15) & ~15; } // tensor-core variants: [TG][R][TP]
+    // Integer variants: one region per pass of phase B.  It holds the accumulate records of the pass's GPASS demos and,
+    // once the pass has consumed them, its part of the slab tile IN THE SAME BYTES (one CTA barrier per pass), so a CTA
+    // needs max(records, tile) instead of records + tile: 22.4 instead of 43 KB at 9x9x9, NPASS = 2.
+    // 9x9x9: the three pieces a phase-B thread reads per term are arrays of their own, X = {pack(w) x 3, u0..u3} at a pitch of
+    // 16 bytes, Y = {u4..u7, u8 v0 v1 v2} at 8 and V = {u8 v0..v2, v3..v6, v7 v8} at 12, so that the records the lanes of a
+    // warp gather (every lane walks its own list of terms) spread over 8 / 16 / 32 bank classes instead of the 4 of one 32-byte
+    // record (ncu: 7.4 + 6.1 + 3.4 shared-memory wavefronts per warp and term against 2.8 + 1.6 + 1.0 without conflicts)
+    static constexpr bool SPLIT = S == 9;
+    static constexpr int REC_SMEM = SPLIT ? 36 : REC; // shared-memory bytes of one accumulate record
+    static __host__ __device__ constexpr int pass_rec(int R) { return GPASS * R * REC_SMEM; }
+    static __host__ __device__ constexpr int pass_stride(int R) { return ((pass_rec(R) > PASS_SLAB ? pass_rec(R) : PASS_SLAB) + 15) & ~15; }
+    static __host__ __device__ constexpr int main_bytes(int R) { return NPASS * pass_stride(R); }
+    // record of (demo g of the tile, term r): byte offset of its pass region and its index in there
+    static __device__ __forceinline__ void rec_pos(int g, int r, int R, int &region, int &k) {
+        const int pass = NPASS == 1 ? 0 : g / GPASS;
+        region = pass * pass_stride(R), k = (g - pass * GPASS) * R + r;
     }
+    static __device__ __forceinline__ int slab_off(int g, int R) { // tile bytes of demo g
+        if constexpr (NPASS == 1) return g * PITCH;
+        const int pass = g / GPASS;
+        return pass * pass_stride(R) + (g - pass * GPASS) * PITCH;
+    }
+    // regions, per-demo flags, work counter + 2 retry-list counters, 2 retry lists of NT entries
     static __host__ __device__ constexpr int smem_bytes(int R) { return main_bytes(R) + TG * 4 + 16 + 2 * NT * 4; }
 };
 
@@ -236,9 +255,9 @@ __device__ __forceinline__ bool draw_triple(uint32_t words[(3 * S + 3) / 4], uin
 
 // token words of one action -> accumulate record: pack(w) in integer form (sum_b (w_b - shift) 256^b per word,
 // bytes beyond S contribute 0) followed by the u, v coefficient bytes (token - shift as int8)
-template <int S, int NT>
-__device__ __forceinline__ void emit_record(const uint32_t words[(3 * S + 3) / 4], int shift, uint32_t *rec) {
-    using C = DemoCfg<S, NT>;
+template <int S, int NT, int NPASS>
+__device__ __forceinline__ void emit_record(const uint32_t words[(3 * S + 3) / 4], int shift, uint8_t *region, int k, int R) {
+    using C = DemoCfg<S, NT, NPASS>;
     constexpr int o = 2 * S;
     constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu;
     const uint32_t sh4 = (uint32_t)shift * ONES4;
@@ -258,7 +277,16 @@ __device__ __forceinline__ void emit_record(const uint32_t words[(3 * S + 3) / 4
     }
 #pragma unroll
     for (int m = 0; m < C::NCW; m++) out[C::KW + m] = ((words[m] | H4) - sh4) ^ H4;
-    if constexpr (C::REC % 16 == 0) {
+    if constexpr (C::SPLIT) {
+        static_assert(!C::SPLIT || (C::KW == 3 && C::NCW == 5), "split records: 9x9x9");
+        const int n = C::GPASS * R;
+        *reinterpret_cast<uint4 *>(region + k * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<uint2 *>(region + n * 16 + k * 8) = make_uint2(out[4], out[5]);
+        uint32_t *v = reinterpret_cast<uint32_t *>(region + n * 24 + k * 12);
+        v[0] = out[5], v[1] = out[6], v[2] = out[7];
+    } else {
+        static_assert(C::REC % 16 == 0, "record pitch");
+        uint8_t *rec = region + k * C::REC;
 #pragma unroll
         for (int m = 0; m < C::REC / 16; m++)
             reinterpret_cast<uint4 *>(rec)[m] = make_uint4(out[4 * m], out[4 * m + 1], out[4 * m + 2], out[4 * m + 3]);
@@ -278,7 +306,7 @@ __device__ __forceinline__ int coef_byte(uint32_t w) {
 // the sampler's integer work and the MMAs overlap.
 // ALIAS: phase A draws under contract v2 (group alias tables, no rejection loop); the categorical thresholds are unused.
 template <int S, int NT, int NPASS, bool SAMPLE, int NTHR, bool GUARD, int MMA = 0, bool ALIAS = false>
-__global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 5 : 4))
+__global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? (NT == 128 ? 8 : NT == 64 ? 16 : 3) : 4))
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
                 long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags,
@@ -286,9 +314,9 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     using C = DemoCfg<S, NT, NPASS>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_rec = smem;  // [TG][R][REC] accumulate records (phases A, B) ...
-    // ... then (OVERLAY) the slab tile [TG][PITCH] (end of B, C) in the same bytes, else a region of its own
-    uint8_t *s_slab = C::OVERLAY ? smem : smem + C::rec_region(R);
+    // integer variants: per pass of phase B one region, first the accumulate records [GPASS][R][REC] (phases A, B), then the
+    // pass's slab tile [GPASS][PITCH] in the same bytes (C::rec_off / C::slab_off); tensor-core variants: records [TG][R][TP]
+    uint8_t *s_rec = smem;
     constexpr int MMA_SCRATCH = MMA > 0 ? (NT / 32) * acc16::WARP_WORDS * 4 : 0; // per-warp H and U2 tables
     uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (MMA == 0 ? C::main_bytes(R) : MMA > 0 ? C::rec_region(R) + MMA_SCRATCH : 0)); // [TG]
     uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
@@ -320,7 +348,11 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
 #pragma unroll
             for (int w = 0; w < G::TP / 16; w++) dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
             if constexpr (MMA == 0) {
-                emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+                {
+                    int region, k;
+                    C::rec_pos(g, r, R, region, k);
+                    emit_record<S, NT, NPASS>(words, shift, smem + region, k, R);
+                }
             } else if constexpr (MMA > 0) {
                 uint4 *rdst = reinterpret_cast<uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
 #pragma unroll
@@ -360,7 +392,11 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                 for (int w = 0; w < G::TP / 16; w++)
                     dst[w] = make_uint4(words[4 * w], words[4 * w + 1], words[4 * w + 2], words[4 * w + 3]);
                 if constexpr (MMA == 0) {
-                    emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+                    {
+                    int region, k;
+                    C::rec_pos(g, r, R, region, k);
+                    emit_record<S, NT, NPASS>(words, shift, smem + region, k, R);
+                }
                 } else if constexpr (MMA > 0) {
                     uint4 *rdst = reinterpret_cast<uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
 #pragma unroll
@@ -449,7 +485,11 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                 const uint4 q = src[w];
                 words[4 * w] = q.x, words[4 * w + 1] = q.y, words[4 * w + 2] = q.z, words[4 * w + 3] = q.w;
             }
-            emit_record<S, NT>(words, shift, reinterpret_cast<uint32_t *>(s_rec + ((size_t)g * R + r) * C::REC));
+            {
+                    int region, k;
+                    C::rec_pos(g, r, R, region, k);
+                    emit_record<S, NT, NPASS>(words, shift, smem + region, k, R);
+                }
         }
     }
     __syncthreads();
@@ -486,11 +526,30 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     // ---------------- B. accumulate the R rank-1 terms in registers
     constexpr int KW = C::KW;
     constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu; // valid bytes of the last word
-    const int j = tid % S;
+    const bool sparse = cat.sparse_terms && R <= 32;
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; pass++) {
-    const int g = pass * C::GPASS + tid / S;
-    const bool worker = tid < C::ACTIVE && g < ng;
+    int gl = tid / S, j = tid % S; // the thread's row: demo gl of the pass, factor index j
+    bool worker = tid < C::ACTIVE && pass * C::GPASS + gl < ng;
+    uint32_t tmask = 0; // sparse: the terms r with v_j != 0
+    if (sparse) {
+        // most coefficients are zero (P(0) = 0.7 in the reference's distributions): a term with v_j = 0 adds nothing to
+        // this thread's entries, so every lane walks only ITS non-zero terms (a bit mask over r, built from the v_j
+        // bytes of the records): ~7 of 23, the warp as many as its busiest lane (~12).  Measured and not kept: loading the
+        // record of the next term before applying the current one (0.792 vs 0.772 ms per 2^20 demos); handing the rows of a
+        // pass to the threads in the order of their term counts (counting sort with match.any + shuffles: 25 % fewer loop
+        // instructions, but the warp with the long rows keeps the CTA's other warps at the pass barrier: 0.805 vs 0.700 ms)
+        if (worker) {
+            const uint8_t *region = smem + pass * C::pass_stride(R);
+            const int8_t *vb = reinterpret_cast<const int8_t *>(
+                C::SPLIT ? region + C::GPASS * R * 24 + gl * R * 12 + 1 + j : region + gl * R * C::REC + 4 * C::KW + S + j);
+            uint32_t bit = 1;
+#pragma unroll 4
+            for (int r = 0; r < R; r++, bit <<= 1)
+                if (vb[r * (C::SPLIT ? 12 : C::REC)] != 0) tmask |= bit;
+        }
+    }
+    const int g = pass * C::GPASS + gl;
     // the sums start at 128 per byte: integer form + H4 = offset-binary bytes, which is what the end of the pass wants
     int32_t acc[S][KW];
 #pragma unroll
@@ -500,17 +559,31 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     uint32_t bad = 0;
     if (worker) {
         int bound = 0;
-        const uint8_t *rec0 = s_rec + (size_t)g * R * C::REC;
-        const int voff = 4 * KW + S + j; // byte offset of v_j in the record
+        const uint8_t *region = smem + pass * C::pass_stride(R);
+        const int k0 = gl * R, nrec = C::GPASS * R; // index of the demo's first record in the region
+        const uint8_t *rec0 = region + k0 * C::REC;                                     // one-piece records
+        const int voff = 4 * KW + S + j;                                                // byte offset of v_j in there
+        const uint8_t *recx = region + k0 * 16, *recy = region + nrec * 16 + k0 * 8;    // split records (C::SPLIT)
+        const int8_t *recv = reinterpret_cast<const int8_t *>(region + nrec * 24 + k0 * 12 + 1 + j);
+        auto v_of = [&](int r) -> int { // v_j of term r
+            if constexpr (C::SPLIT) return (int)recv[r * 12];
+            else return (int)reinterpret_cast<const int8_t *>(rec0 + (size_t)r * C::REC)[voff];
+        };
         // one term: acc[i][.] += u_i * (v_j * pack(w))
         auto load_rec = [&](int r, uint32_t (&q)[C::REC / 4], int &vj) {
-            const uint8_t *rec = rec0 + (size_t)r * C::REC;
+            if constexpr (C::SPLIT) {
+                const uint4 x = *reinterpret_cast<const uint4 *>(recx + r * 16);
+                const uint2 y = *reinterpret_cast<const uint2 *>(recy + r * 8);
+                q[0] = x.x, q[1] = x.y, q[2] = x.z, q[3] = x.w, q[4] = y.x, q[5] = y.y;
+            } else {
+                const uint8_t *rec = rec0 + (size_t)r * C::REC;
 #pragma unroll
-            for (int m = 0; m < C::REC / 16; m++) {
-                const uint4 v4 = reinterpret_cast<const uint4 *>(rec)[m];
-                q[4 * m] = v4.x, q[4 * m + 1] = v4.y, q[4 * m + 2] = v4.z, q[4 * m + 3] = v4.w;
+                for (int m = 0; m < C::REC / 16; m++) {
+                    const uint4 v4 = reinterpret_cast<const uint4 *>(rec)[m];
+                    q[4 * m] = v4.x, q[4 * m + 1] = v4.y, q[4 * m + 2] = v4.z, q[4 * m + 3] = v4.w;
+                }
             }
-            vj = (int)reinterpret_cast<const int8_t *>(rec)[voff];
+            vj = v_of(r);
         };
         auto apply_rec = [&](const uint32_t (&q)[C::REC / 4], int vj) {
             if constexpr (GUARD) bound += abs(vj);
@@ -530,15 +603,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                 for (int m = 0; m < KW; m++) acc[i][m] += ui * vw[m];
             }
         };
-        if (cat.sparse_terms && R <= 32) {
-            // most coefficients are zero (P(0) = 0.7 in the reference's distributions): a term with v_j = 0 adds nothing to
-            // this thread's entries, so every lane walks only ITS non-zero terms (a bit mask over r, built from the v_j
-            // bytes of the records); the warp runs max-over-lanes iterations (~12 of 23) instead of R.  (Loading the record of
-            // the next term before applying the current one was measured: 0.792 vs 0.772 ms per 2^20 demos -- not kept.)
-            uint32_t tmask = 0, bit = 1;
-#pragma unroll 4
-            for (int r = 0; r < R; r++, bit <<= 1)
-                if (reinterpret_cast<const int8_t *>(rec0 + (size_t)r * C::REC)[voff] != 0) tmask |= bit;
+        if (sparse) {
             while (tmask) {
                 uint32_t q[C::REC / 4];
                 int vj;
@@ -569,10 +634,12 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                         int e = 0;
 #pragma unroll 1
                         for (int r = 0; r < R; r++) {
-                            const uint8_t *rec = rec0 + (size_t)r * C::REC;
-                            const int8_t *cb = reinterpret_cast<const int8_t *>(rec) + 4 * KW;
-                            const uint32_t wb = (reinterpret_cast<const uint32_t *>(rec)[m] + H4) ^ H4; // integer form -> bytes
-                            e += (int)cb[i] * (int)cb[S + j] * (int)(int8_t)((wb >> (8 * kk)) & 0xFFu);
+                            uint32_t q[C::REC / 4];
+                            int vj;
+                            load_rec(r, q, vj);
+                            const uint32_t wb = (q[m] + H4) ^ H4; // integer form -> bytes
+                            const int ui = (int)(int8_t)((q[KW + (i >> 2)] >> (8 * (i & 3))) & 0xFFu);
+                            e += ui * vj * (int)(int8_t)((wb >> (8 * kk)) & 0xFFu);
                         }
                         if (e < -64 || e > 63) bad = 1;
                         word |= ((uint32_t)e & 0xFFu) << (8 * kk);
@@ -594,7 +661,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
             bad = ~ok & H4;
         }
     }
-    if constexpr (C::OVERLAY) __syncthreads(); // every record has been consumed: the slab tile takes over the same bytes
+    if constexpr (C::TILE) __syncthreads(); // every record of the pass has been consumed: its slab tile takes over the same bytes
     if constexpr (S == 4) {
         // 4x4x4: a game is 64 bytes and thread j holds one aligned word of each of its four rows: straight to HBM (the four
         // threads of a game fill 16 contiguous bytes per store; a bulk store per 64-byte game costs ~10 warp-instructions)
@@ -607,7 +674,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     } else if (worker) {
         // registers -> slab tile: entry (i, j, k) is byte i*RP + j*S + k; the last j also zeroes the row padding,
         // j = 0 the game padding
-        uint8_t *gbase = s_slab + (size_t)g * C::PITCH + j * S;
+        uint8_t *gbase = smem + pass * C::pass_stride(R) + gl * C::PITCH + j * S;
 #pragma unroll
         for (int i = 0; i < S; i++) {
             if constexpr (S == 9) {
@@ -652,7 +719,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
 
     // ---------------- C. tile out: one bulk store per game (S = 4 wrote its games from registers)
     if constexpr (S != 4) {
-        for (int gg = tid; gg < ng; gg += NT) bulk_s2g(slab + (g0 + gg) * G::GP, s_slab + (size_t)gg * C::PITCH, (uint32_t)G::GP);
+        for (int gg = tid; gg < ng; gg += NT) bulk_s2g(slab + (g0 + gg) * G::GP, smem + C::slab_off(gg, R), (uint32_t)G::GP);
         if (tid < ng) bulk_commit();
     }
     if (flags)

@@ -1,4 +1,4 @@
-"""One launch set of a round-2 kernel at bench size (for ncu): python scripts/prof_r2.py sample|basis9|basis16|basis4|demo9|demo4|demo16|step|rollout|rank|expand"""
+"""One launch set of a round-2 kernel at bench size (for ncu): python scripts/prof_r2.py sample|basis9|basis16|basis4|demo9|demo4|demo16|acc9|acc4|step|rollout|rank|expand"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -21,6 +21,14 @@ elif which.startswith("basis"):
     out = torch.empty(slab.shape, dtype=torch.int16, device="cuda")
     for _ in range(3):
         env.change_of_basis(slab, mats, S, out=out)
+elif which.startswith("acc"):
+    S = int(which[3:])
+    R, N = {4: (7, 1 << 22), 9: (23, 1 << 20), 16: (49, 1 << 17)}[S]
+    vals, probs, shift = ((-1, 0, 1), (0.15, 0.7, 0.15), 1) if S == 4 else (V5, P5, 2)
+    tape, slab, _ = env.make_synthetic_demos(N, R, S, vals, probs, shift, seed=1)
+    out = torch.empty_like(slab)
+    for _ in range(3):
+        env.accumulate_demos(tape, S, shift, slab=out)
 elif which.startswith("demo"):
     S = int(which[4:])
     R, N = {4: (7, 1 << 22), 9: (23, 1 << 20), 16: (49, 1 << 17)}[S]
