@@ -30,6 +30,7 @@
 //      path and the (rare) thread above it recomputes its entries one by one.
 //   C. the slab tile leaves through one TMA bulk store.
 #include <cstring>
+#include <mutex>
 
 #include "tg_demo_mma.cuh"
 #include "tg_step.cuh"
@@ -76,6 +77,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // the probability that the rest of the factor is zero too.  No rejection loop, half the Philox blocks of the thresholded
 // contract, and no comparisons per token.
 constexpr int ALIAS_BUCKETS = 128;
+// the tables in the contract's own terms (host side: built by build_alias, exported by tg_demo_alias_tables)
 struct AliasParams {
     uint16_t tab[8][ALIAS_BUCKETS]; // [g] tilted table of group g (g < NG <= 6), [6] plain size 3, [7] plain size 1
     uint32_t lut3[ALIAS_BUCKETS];   // outcome of a size-3 group -> its three tokens (bytes 0..2)
@@ -83,33 +85,74 @@ struct AliasParams {
     uint32_t zo3, zo1;              // the all-zero outcomes (255 if 0 is not in the alphabet)
     uint32_t rk[10][2];             // Philox round keys
 };
+// The same tables in the form the kernel reads.  A bucket is ONE word that already holds both of its outcomes as PRMT
+// selectors: bits 0..11 its own outcome, bits 12..23 its alias, each three nibbles = the value indices of the group's three
+// entries (7 = "no entry": byte 7 of the token LUT is 0), bits 23..31 the 9-bit threshold (bit 23 is shared with the top bit
+// of the last alias nibble, which a selector never uses: the kernel masks with 0x777).  The chosen selector | 0x7000 turns
+// the 8-byte token LUT (two registers) into the group's token bytes with one PRMT -- no outcome -> token table in shared
+// memory, and since a factor's groups are drawn in order ("all zero so far" selects the tilted or the plain table by
+// ADDRESS), one 4-byte load per group instead of two bucket loads and a LUT load.
+// The tables live in a small per-device cache in global memory (alias_device_tables below) and every CTA copies them to
+// shared memory with coalesced 16-byte loads; as kernel parameters each CTA paid one SERIALISED constant-bank read per
+// word (lanes of a warp read different words): ~23 SM-cycles per 9x9x9 demo.
+struct AliasTabs {
+    uint32_t tab[8][ALIAS_BUCKETS]; // same table order as AliasParams::tab
+};
+struct AliasDev {
+    const uint32_t *tab;            // device copy of an AliasTabs
+    uint32_t lut_lo, lut_hi;        // token (value + shift) of value index 0..3 | 4..7 (unused indices: 0)
+    uint32_t zsel3, zsel1;          // selector | 0x7000 of the all-zero outcome (0xFFFFFFFF if 0 is not in the alphabet)
+    uint32_t rk[10][2];             // Philox round keys
+};
 template <int S>
 struct AliasGeo {
     static constexpr int NG = (S + 2) / 3, LAST = S - 3 * (NG - 1); // groups per factor, size of the last one (1 or 3)
     static constexpr int ND = 3 * NG, NB = (ND + 7) / 8;             // 16-bit draws and Philox blocks per triple
-    static constexpr int TAB_WORDS = (NG + 2) * ALIAS_BUCKETS / 2;   // shared-memory copy: tables [0..NG), plain 3, plain 1
-    static constexpr int SMEM_BYTES = TAB_WORDS * 4 + ALIAS_BUCKETS * 4 + 32;
+    static constexpr int TAB_WORDS = (NG + 2) * ALIAS_BUCKETS;       // shared-memory copy: tables [0..NG), plain 3, plain 1
+    static constexpr int SMEM_BYTES = TAB_WORDS * 4;
     static_assert(LAST == 1 || LAST == 3, "group sizes 3 and 1 only");
+    static constexpr __host__ __device__ bool three(int g) { return g < NG - 1 || LAST == 3; }
+    // Token word w of the action record (bytes 4w .. 4w+3 of cat(u, v, w)) is one PRMT of the token words of the (at most
+    // two) groups it overlaps: group index of its first / last byte and the selector (nibble b: byte of the first group,
+    // 4 + byte of the second, 3 = the always-zero top byte of a group's token word for the padding beyond 3S)
+    static constexpr __host__ __device__ int group_of(int q) { return (q / S) * NG + ((q % S) / 3 < NG ? (q % S) / 3 : NG - 1); }
+    static constexpr __host__ __device__ int group_byte0(int m) { return (m / NG) * S + 3 * (m % NG); }
+    static constexpr __host__ __device__ int word_first(int w) { return group_of(4 * w); }
+    static constexpr __host__ __device__ int word_last(int w) { return group_of(4 * w + 3 < 3 * S ? 4 * w + 3 : 3 * S - 1); }
+    static constexpr __host__ __device__ uint32_t word_sel(int w) {
+        uint32_t sel = 0;
+        for (int b = 0; b < 4; b++) {
+            const int q = 4 * w + b;
+            uint32_t nib = 3;
+            if (q < 3 * S) nib = group_of(q) == word_first(w) ? (uint32_t)(q - group_byte0(word_first(w))) : 4u + (uint32_t)(q - group_byte0(word_last(w)));
+            sel |= nib << (4 * b);
+        }
+        return sel;
+    }
+    static constexpr __host__ __device__ bool words_ok() { // every byte of a word belongs to its first or its last group
+        for (int q = 0; q < 3 * S; q++)
+            if (group_of(q) != word_first(q / 4) && group_of(q) != word_last(q / 4)) return false;
+        return true;
+    }
 };
 
-// CTA-wide copy of the tables from the kernel parameters (constant bank) to shared memory
+// CTA-wide copy of the tables from global memory (L2-resident: every CTA reads the same 2-4 KB) to shared memory
 template <int S, int NT>
-__device__ __forceinline__ void alias_to_smem(const AliasParams &ap, uint32_t *s_alias) {
+__device__ __forceinline__ void alias_to_smem(const AliasDev &ap, uint32_t *s_alias) {
     using A = AliasGeo<S>;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(ap.tab);
-    for (int w = threadIdx.x; w < A::NG * (ALIAS_BUCKETS / 2); w += NT) s_alias[w] = src[w];
-    for (int w = threadIdx.x; w < ALIAS_BUCKETS; w += NT) s_alias[A::NG * (ALIAS_BUCKETS / 2) + w] = src[6 * (ALIAS_BUCKETS / 2) + w]; // plain 3, plain 1
-    for (int w = threadIdx.x; w < ALIAS_BUCKETS + 8; w += NT) s_alias[A::TAB_WORDS + w] = w < ALIAS_BUCKETS ? ap.lut3[w] : ap.lut1[w - ALIAS_BUCKETS];
+    const uint4 *src = reinterpret_cast<const uint4 *>(ap.tab);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_alias);
+    for (int w = threadIdx.x; w < A::NG * (ALIAS_BUCKETS / 4); w += NT) dst[w] = __ldg(src + w);
+    for (int w = threadIdx.x; w < 2 * (ALIAS_BUCKETS / 4); w += NT) dst[A::NG * (ALIAS_BUCKETS / 4) + w] = __ldg(src + 6 * (ALIAS_BUCKETS / 4) + w); // plain 3, plain 1
 }
 
 // one factor triple (3S tokens) of demo (d_lo, d_hi), term r under contract v2
 template <int S>
 __device__ __forceinline__ void draw_triple_alias(uint32_t words[(3 * S + 3) / 4], uint32_t d_lo, uint32_t d_hi, int r,
-                                                  const AliasParams &ap, const uint32_t *s_alias) {
+                                                  const AliasDev &ap, const uint32_t *s_alias) {
     using A = AliasGeo<S>;
     constexpr int NW = (3 * S + 3) / 4;
-    const uint16_t *s_tab = reinterpret_cast<const uint16_t *>(s_alias);
-    const uint32_t *s_lut3 = s_alias + A::TAB_WORDS, *s_lut1 = s_lut3 + ALIAS_BUCKETS;
+    static_assert(A::words_ok(), "a token word overlaps more than two groups");
     uint32_t blk[4 * A::NB];
 #pragma unroll
     for (int b = 0; b < A::NB; b++) {
@@ -121,40 +164,26 @@ __device__ __forceinline__ void draw_triple_alias(uint32_t words[(3 * S + 3) / 4
         }
         blk[4 * b] = c0, blk[4 * b + 1] = c1, blk[4 * b + 2] = c2, blk[4 * b + 3] = c3;
     }
+    // draw m = f * NG + g is half (m & 1) of Philox word m >> 1; the three factors are independent chains of NG loads
+    uint32_t tk[A::ND];
+    const uint8_t *s_tab = reinterpret_cast<const uint8_t *>(s_alias);
+    bool az[3] = {true, true, true}; // every group of the factor so far is all zero
 #pragma unroll
-    for (int w = 0; w < NW; w++) words[w] = 0;
-    // both candidate buckets of every group first (the tilted table of its position and the plain table): their loads do
-    // not depend on each other, only the choice between them follows the factor's "all zero so far" chain
-    uint32_t h[A::ND], bt[A::ND], bp[A::ND];
+    for (int g = 0; g < A::NG; g++) {
 #pragma unroll
-    for (int m = 0; m < A::ND; m++) {
-        const int g = m % A::NG;
-        const bool three = g < A::NG - 1 || A::LAST == 3;
-        h[m] = (m & 1) ? (blk[m >> 1] >> 16) : (blk[m >> 1] & 0xFFFFu);
-        bt[m] = s_tab[g * ALIAS_BUCKETS + (h[m] & 127u)];
-        bp[m] = g == 0 ? 0u : s_tab[(three ? A::NG : A::NG + 1) * ALIAS_BUCKETS + (h[m] & 127u)];
-    }
-    uint32_t o[A::ND];
-#pragma unroll
-    for (int f = 0; f < 3; f++) {
-        bool az = true; // every group of this factor so far is all zero
-#pragma unroll
-        for (int g = 0; g < A::NG; g++) {
+        for (int f = 0; f < 3; f++) {
             const int m = f * A::NG + g;
-            const bool three = g < A::NG - 1 || A::LAST == 3;
-            const uint32_t bucket = (g == 0 || az) ? bt[m] : bp[m];
-            o[m] = ((h[m] >> 7) < (bucket & 511u)) ? (h[m] & 127u) : (bucket >> 9);
-            az = az && (o[m] == (three ? ap.zo3 : ap.zo1));
+            const uint32_t h = (m & 1) ? (blk[m >> 1] >> 16) : (blk[m >> 1] & 0xFFFFu);
+            const int tilted = g * ALIAS_BUCKETS * 4, plain = (A::three(g) ? A::NG : A::NG + 1) * ALIAS_BUCKETS * 4;
+            const uint32_t e = *reinterpret_cast<const uint32_t *>(s_tab + ((g == 0 || az[f]) ? tilted : plain) + 4 * (h & 127u));
+            const uint32_t sel = ((((h >> 7) < (e >> 23)) ? e : (e >> 12)) & 0x777u) | 0x7000u;
+            tk[m] = prmt(ap.lut_lo, ap.lut_hi, sel);
+            az[f] = az[f] && sel == (A::three(g) ? ap.zsel3 : ap.zsel1);
         }
     }
 #pragma unroll
-    for (int m = 0; m < A::ND; m++) {
-        const int f = m / A::NG, g = m % A::NG;
-        const bool three = g < A::NG - 1 || A::LAST == 3;
-        const uint32_t tk = three ? s_lut3[o[m]] : s_lut1[o[m]];
-        const int B = f * S + 3 * g; // byte offset of the group in the record
-        words[B >> 2] |= tk << (8 * (B & 3));
-        if ((B & 3) + (three ? 3 : 1) > 4) words[(B >> 2) + 1] |= tk >> (32 - 8 * (B & 3));
+    for (int w = 0; w < NW; w++) {
+        words[w] = prmt(tk[A::word_first(w)], tk[A::word_last(w)], A::word_sel(w));
     }
 }
 
@@ -255,7 +284,8 @@ __device__ __forceinline__ bool draw_triple(uint32_t words[(3 * S + 3) / 4], uin
 
 // token words of one action -> accumulate record: pack(w) in integer form (sum_b (w_b - shift) 256^b per word,
 // bytes beyond S contribute 0) followed by the u, v coefficient bytes (token - shift as int8)
-template <int S, int NT, int NPASS>
+// SMALL: every token is below 128 + shift (sampled tokens are <= 2 * shift): the per-byte subtraction needs no guard bit
+template <int S, int NT, int NPASS, bool SMALL>
 __device__ __forceinline__ void emit_record(const uint32_t words[(3 * S + 3) / 4], int shift, uint8_t *region, int k, int R) {
     using C = DemoCfg<S, NT, NPASS>;
     constexpr int o = 2 * S;
@@ -276,7 +306,7 @@ __device__ __forceinline__ void emit_record(const uint32_t words[(3 * S + 3) / 4
         out[m] = (wt & msk) - (sh4 & msk);
     }
 #pragma unroll
-    for (int m = 0; m < C::NCW; m++) out[C::KW + m] = ((words[m] | H4) - sh4) ^ H4;
+    for (int m = 0; m < C::NCW; m++) out[C::KW + m] = SMALL ? (words[m] + (H4 - sh4)) ^ H4 : ((words[m] | H4) - sh4) ^ H4;
     if constexpr (C::SPLIT) {
         static_assert(!C::SPLIT || (C::KW == 3 && C::NCW == 5), "split records: 9x9x9");
         const int n = C::GPASS * R;
@@ -310,7 +340,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     demo_kernel(unsigned long long first_demo, long long N, int R, uint32_t magic_r, int shift,
                 const __grid_constant__ Categorical cat, int max_tries, uint8_t *__restrict__ tape,
                 long long tape_step_stride, int8_t *__restrict__ slab, uint8_t *__restrict__ flags,
-                const __grid_constant__ AliasParams ap) {
+                const __grid_constant__ AliasDev ap) {
     using C = DemoCfg<S, NT, NPASS>;
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -351,7 +381,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                 {
                     int region, k;
                     C::rec_pos(g, r, R, region, k);
-                    emit_record<S, NT, NPASS>(words, shift, smem + region, k, R);
+                    emit_record<S, NT, NPASS, true>(words, shift, smem + region, k, R);
                 }
             } else if constexpr (MMA > 0) {
                 uint4 *rdst = reinterpret_cast<uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
@@ -395,7 +425,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
                     {
                     int region, k;
                     C::rec_pos(g, r, R, region, k);
-                    emit_record<S, NT, NPASS>(words, shift, smem + region, k, R);
+                    emit_record<S, NT, NPASS, false>(words, shift, smem + region, k, R);
                 }
                 } else if constexpr (MMA > 0) {
                     uint4 *rdst = reinterpret_cast<uint4 *>(s_rec + ((size_t)g * R + r) * G::TP);
@@ -488,7 +518,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
             {
                     int region, k;
                     C::rec_pos(g, r, R, region, k);
-                    emit_record<S, NT, NPASS>(words, shift, smem + region, k, R);
+                    emit_record<S, NT, NPASS, false>(words, shift, smem + region, k, R);
                 }
         }
     }
@@ -525,7 +555,6 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
 
     // ---------------- B. accumulate the R rank-1 terms in registers
     constexpr int KW = C::KW;
-    constexpr uint32_t WLAST = (S % 4) ? (0xFFFFFFFFu >> (8 * (4 - S % 4))) : 0xFFFFFFFFu; // valid bytes of the last word
     const bool sparse = cat.sparse_terms && R <= 32;
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; pass++) {
@@ -739,7 +768,7 @@ static int launch_demo(unsigned long long first, long long N, int R, int shift, 
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R); // ceil(2^32 / R)
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
-    static const AliasParams no_alias = {};
+    static const AliasDev no_alias = {};
     if (guard) {
         auto kern = demo_kernel<S, NT, NPASS, SAMPLE, NTHR, true>;
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -763,7 +792,7 @@ static int launch_demo16_mma(unsigned long long first, long long N, int R, int s
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
     const long long grid = (N + C::TG - 1) / C::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
-    static const AliasParams no_alias = {};
+    static const AliasDev no_alias = {};
     auto kern = demo_kernel<16, NT, NPASS, true, NTHR, false, MMA>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(int)grid, NT, smem, st>>>(first, N, R, magic, shift, cat, max_tries, tape, stride, slab, flags, no_alias);
@@ -773,7 +802,7 @@ static int launch_demo16_mma(unsigned long long first, long long N, int R, int s
 
 // ---- contract v2 launches (the measured-best tile shapes of each size, phase A on the alias tables)
 template <int S, int NT, int NPASS, int MMA>
-static int launch_demo_alias(unsigned long long first, long long N, int R, int shift, const Categorical &cat, const AliasParams &ap,
+static int launch_demo_alias(unsigned long long first, long long N, int R, int shift, const Categorical &cat, const AliasDev &ap,
                              uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     using C = DemoCfg<S, NT, NPASS>;
     constexpr int TAIL = MMA > 0 ? 2 * NT * 4 : (2 * NT * 4 > AliasGeo<S>::SMEM_BYTES ? 2 * NT * 4 : AliasGeo<S>::SMEM_BYTES);
@@ -798,7 +827,7 @@ static int launch_demo_alias(unsigned long long first, long long N, int R, int s
 }
 
 static int dispatch_demo_alias(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
-                               const AliasParams &ap, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
+                               const AliasDev &ap, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     switch (S) {
     case 4:
         if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
@@ -896,6 +925,83 @@ static void build_alias(const int8_t *values, const double *probs, int n, int S,
         A.rk[r][0] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
         A.rk[r][1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
+}
+
+// the tables as the kernel reads them (AliasDev)
+static void alias_to_dev(const AliasParams &A, const int8_t *values, int n, int S, int shift, AliasTabs &T, AliasDev &D) {
+    const int ng = (S + 2) / 3, last = S - 3 * (ng - 1);
+    D = AliasDev{};
+    T = AliasTabs{};
+    auto sel = [&](int o, int size) -> uint32_t {
+        if (size == 3) return o < n * n * n ? (uint32_t)(o % n) | ((uint32_t)((o / n) % n) << 4) | ((uint32_t)(o / (n * n)) << 8) : 0x777u;
+        return o < n ? (uint32_t)o | 0x770u : 0x777u;
+    };
+    for (int t = 0; t < 8; t++) {
+        const int size = t < 6 ? (t < ng ? (t < ng - 1 ? 3 : last) : 0) : (t == 6 ? 3 : 1);
+        if (!size) continue;
+        for (int b = 0; b < ALIAS_BUCKETS; b++) {
+            const uint32_t thr = A.tab[t][b] & 511u, al = A.tab[t][b] >> 9;
+            T.tab[t][b] = sel(b, size) | (sel((int)al, size) << 12) | (thr << 23);
+        }
+    }
+    int z = -1;
+    for (int i = 0; i < n; i++) {
+        (i < 4 ? D.lut_lo : D.lut_hi) |= ((uint32_t)(values[i] + shift) & 0xFFu) << (8 * (i & 3));
+        if (values[i] == 0 && z < 0) z = i;
+    }
+    D.zsel3 = z >= 0 ? ((uint32_t)z * 0x111u) | 0x7000u : 0xFFFFFFFFu;
+    D.zsel1 = z >= 0 ? (uint32_t)z | 0x7770u : 0xFFFFFFFFu;
+    memcpy(D.rk, A.rk, sizeof(D.rk));
+}
+
+// ---- per-device cache of device-format tables (static device memory: the library still allocates nothing).  A table set
+// is uploaded by a one-CTA kernel on the caller's stream the first time it is asked for; a later launch -- on any stream --
+// waits for that upload's event.  Eight sets per device; a ninth distinct set evicts the least recently used one after a
+// cudaDeviceSynchronize (kernels of other streams may still be reading it) -- a training run uses one or two.
+constexpr int ALIAS_SLOTS = 8, ALIAS_MAXDEV = 64;
+__device__ __align__(16) uint32_t g_alias_tab[ALIAS_SLOTS][8 * ALIAS_BUCKETS];
+__global__ void alias_upload_kernel(const __grid_constant__ AliasTabs t, int slot) {
+    for (int w = threadIdx.x; w < 8 * ALIAS_BUCKETS; w += blockDim.x) g_alias_tab[slot][w] = (&t.tab[0][0])[w];
+}
+struct AliasSlot {
+    bool valid = false;
+    AliasTabs host;
+    cudaEvent_t ready = nullptr;
+    unsigned long long stamp = 0;
+};
+static AliasSlot g_alias_slots[ALIAS_MAXDEV][ALIAS_SLOTS];
+static std::mutex g_alias_mu;
+static unsigned long long g_alias_stamp = 0;
+
+static int alias_device_tables(const AliasTabs &want, cudaStream_t st, const uint32_t **dptr) {
+    int dev = 0;
+    TG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= ALIAS_MAXDEV) return TG_E_ARG;
+    uint32_t *base = nullptr;
+    TG_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_alias_tab));
+    std::lock_guard<std::mutex> lock(g_alias_mu);
+    AliasSlot *slots = g_alias_slots[dev];
+    int hit = -1, lru = -1; // lru: the first free slot, else the least recently used one
+    for (int i = 0; i < ALIAS_SLOTS; i++) {
+        if (slots[i].valid && memcmp(&slots[i].host, &want, sizeof(AliasTabs)) == 0) hit = i;
+        if (lru < 0 || (slots[lru].valid && (!slots[i].valid || slots[i].stamp < slots[lru].stamp))) lru = i;
+    }
+    if (hit < 0) {
+        AliasSlot &sl = slots[lru];
+        if (sl.valid) TG_CUDA(cudaDeviceSynchronize()); // eviction: nobody may still be reading the old tables
+        if (!sl.ready) TG_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+        sl.valid = false;
+        alias_upload_kernel<<<1, 256, 0, st>>>(want, lru);
+        TG_CUDA(cudaGetLastError());
+        TG_CUDA(cudaEventRecord(sl.ready, st));
+        sl.host = want, sl.valid = true;
+        hit = lru;
+    } else {
+        TG_CUDA(cudaStreamWaitEvent(st, slots[hit].ready, 0));
+    }
+    slots[hit].stamp = ++g_alias_stamp;
+    *dptr = base + (size_t)hit * 8 * ALIAS_BUCKETS;
+    return TG_OK;
 }
 
 template <int NTHR>
@@ -1014,7 +1120,12 @@ int tg_demo_gen_philox(uint64_t seed, uint64_t first_demo, int64_t N, int R, int
     if (tg::alias_applies(values, probs, n_values, S)) {
         tg::AliasParams ap;
         tg::build_alias(values, probs, n_values, S, shift, seed, ap);
-        return tg::dispatch_demo_alias(first_demo, N, R, S, shift, cat, ap, tape, tape_step_stride, slab, flags, st);
+        tg::AliasTabs tabs;
+        tg::AliasDev dev;
+        tg::alias_to_dev(ap, values, n_values, S, shift, tabs, dev);
+        const int rc = tg::alias_device_tables(tabs, st, &dev.tab);
+        if (rc != TG_OK) return rc;
+        return tg::dispatch_demo_alias(first_demo, N, R, S, shift, cat, dev, tape, tape_step_stride, slab, flags, st);
     }
     // 16x16x16, R <= 64: the targets are summed on the tensor cores (tg_demo_mma.cuh) inside the sampling kernel;
     // TG_DEMO_MMA=0 keeps the packed-IMAD accumulation (A/B timing only)
