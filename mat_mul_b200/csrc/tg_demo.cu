@@ -88,7 +88,7 @@ struct AliasParams {
 // The same tables in the form the kernel reads.  A bucket is ONE word that already holds both of its outcomes as PRMT
 // selectors: bits 0..11 its own outcome, bits 12..23 its alias, each three nibbles = the value indices of the group's three
 // entries (7 = "no entry": byte 7 of the token LUT is 0), bits 23..31 the 9-bit threshold (bit 23 is shared with the top bit
-// of the last alias nibble, which a selector never uses: the kernel masks with 0x777).  The chosen selector | 0x7000 turns
+// of the last alias nibble, which a selector never uses: the kernel masks with 0x777).  The chosen selector turns
 // the 8-byte token LUT (two registers) into the group's token bytes with one PRMT -- no outcome -> token table in shared
 // memory, and since a factor's groups are drawn in order ("all zero so far" selects the tilted or the plain table by
 // ADDRESS), one 4-byte load per group instead of two bucket loads and a LUT load.
@@ -101,7 +101,7 @@ struct AliasTabs {
 struct AliasDev {
     const uint32_t *tab;            // device copy of an AliasTabs
     uint32_t lut_lo, lut_hi;        // token (value + shift) of value index 0..3 | 4..7 (unused indices: 0)
-    uint32_t zsel3, zsel1;          // selector | 0x7000 of the all-zero outcome (0xFFFFFFFF if 0 is not in the alphabet)
+    uint32_t zsel3, zsel1;          // selector of the all-zero outcome (0xFFFFFFFF if 0 is not in the alphabet)
     uint32_t rk[10][2];             // Philox round keys
 };
 template <int S>
@@ -164,7 +164,9 @@ __device__ __forceinline__ void draw_triple_alias(uint32_t words[(3 * S + 3) / 4
         }
         blk[4 * b] = c0, blk[4 * b + 1] = c1, blk[4 * b + 2] = c2, blk[4 * b + 3] = c3;
     }
-    // draw m = f * NG + g is half (m & 1) of Philox word m >> 1; the three factors are independent chains of NG loads
+    // draw m = f * NG + g is half (m & 1) of Philox word m >> 1, moved to the top of a register: bucket = bits 16..22,
+    // "draw >> 7 < threshold" is one unsigned compare with the bucket word's threshold bits (the bits below bit 23 of the
+    // draw cannot change it).  The three factors are independent chains of NG loads.
     uint32_t tk[A::ND];
     const uint8_t *s_tab = reinterpret_cast<const uint8_t *>(s_alias);
     bool az[3] = {true, true, true}; // every group of the factor so far is all zero
@@ -173,18 +175,21 @@ __device__ __forceinline__ void draw_triple_alias(uint32_t words[(3 * S + 3) / 4
 #pragma unroll
         for (int f = 0; f < 3; f++) {
             const int m = f * A::NG + g;
-            const uint32_t h = (m & 1) ? (blk[m >> 1] >> 16) : (blk[m >> 1] & 0xFFFFu);
-            const int tilted = g * ALIAS_BUCKETS * 4, plain = (A::three(g) ? A::NG : A::NG + 1) * ALIAS_BUCKETS * 4;
-            const uint32_t e = *reinterpret_cast<const uint32_t *>(s_tab + ((g == 0 || az[f]) ? tilted : plain) + 4 * (h & 127u));
-            const uint32_t sel = ((((h >> 7) < (e >> 23)) ? e : (e >> 12)) & 0x777u) | 0x7000u;
-            tk[m] = prmt(ap.lut_lo, ap.lut_hi, sel);
+            const uint32_t x = (m & 1) ? blk[m >> 1] : (blk[m >> 1] << 16);
+            const uint32_t idx4 = (x >> 14) & 0x1FCu;
+            const int tilted = g * ALIAS_BUCKETS * 4;
+            const int plain = (A::three(g) ? A::NG : A::NG + 1) * ALIAS_BUCKETS * 4;
+            uint32_t e;
+            if (g == 0 || az[f]) e = *reinterpret_cast<const uint32_t *>(s_tab + tilted + idx4);
+            else e = *reinterpret_cast<const uint32_t *>(s_tab + plain + idx4);
+            const uint32_t sel = ((x < (e & 0xFF800000u)) ? e : (e >> 12)) & 0x777u;
+            tk[m] = prmt(ap.lut_lo, ap.lut_hi, sel); // bytes 0..2 (size 1: byte 0) are tokens, the rest is not used
             az[f] = az[f] && sel == (A::three(g) ? ap.zsel3 : ap.zsel1);
         }
     }
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
-        words[w] = prmt(tk[A::word_first(w)], tk[A::word_last(w)], A::word_sel(w));
-    }
+    for (int w = 0; w < NW; w++) words[w] = prmt(tk[A::word_first(w)], tk[A::word_last(w)], A::word_sel(w));
+    if constexpr ((3 * S) % 4 != 0) words[NW - 1] &= 0xFFFFFFFFu >> (8 * (4 - (3 * S) % 4)); // tape padding stays zero
 }
 
 template <int S, int NT, int NPASS = 1>
@@ -636,8 +641,9 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
             while (tmask) {
                 uint32_t q[C::REC / 4];
                 int vj;
-                load_rec(__ffs((int)tmask) - 1, q, vj);
-                tmask &= tmask - 1;
+                const int t = 31 - __clz((int)tmask); // the terms in any order: the highest set bit is one FLO
+                load_rec(t, q, vj);
+                tmask ^= 1u << t;
                 apply_rec(q, vj);
             }
         } else {
@@ -949,8 +955,8 @@ static void alias_to_dev(const AliasParams &A, const int8_t *values, int n, int 
         (i < 4 ? D.lut_lo : D.lut_hi) |= ((uint32_t)(values[i] + shift) & 0xFFu) << (8 * (i & 3));
         if (values[i] == 0 && z < 0) z = i;
     }
-    D.zsel3 = z >= 0 ? ((uint32_t)z * 0x111u) | 0x7000u : 0xFFFFFFFFu;
-    D.zsel1 = z >= 0 ? (uint32_t)z | 0x7770u : 0xFFFFFFFFu;
+    D.zsel3 = z >= 0 ? (uint32_t)z * 0x111u : 0xFFFFFFFFu;
+    D.zsel1 = z >= 0 ? (uint32_t)z | 0x770u : 0xFFFFFFFFu;
     memcpy(D.rk, A.rk, sizeof(D.rk));
 }
 
