@@ -1,4 +1,5 @@
 // tg_aux.cu -- K4 demo_sample (training-sample batcher), K6 slice_rank, K7 state_key.
+#include <mutex>
 #include <type_traits>
 
 #include "tg_step.cuh"
@@ -493,15 +494,18 @@ template <bool TGT16, bool PACK16>
 __global__ void __launch_bounds__(32 * WARPS, 4)
     demo_sample_rows9_kernel(const uint8_t *__restrict__ tape_dm, const uint8_t *__restrict__ targets, long long N, int R, int dim_t,
                              int replay_shift, const long long *__restrict__ idx, long long nb, float *__restrict__ states,
-                             float *__restrict__ scalars, long long *__restrict__ actions, float *__restrict__ rewards) {
+                             float *__restrict__ scalars, long long *__restrict__ actions, float *__restrict__ rewards,
+                             unsigned long long *__restrict__ ticket) {
     static_assert(PACK16, "the row kernel keeps 16-bit lanes; the host routes larger bounds to the column kernel");
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *s_rec = smem + (size_t)warp * warp_bytes(R);
     float *s_tile = reinterpret_cast<float *>(s_rec + ((SPW * R * RECB + 15) & ~15));
-    // a warp walks triples of samples trip, trip + nwarps, ...: the index of the NEXT triple is read while this one is
-    // processed, and its records and target rows are pulled into L2 before the slots of this one are built, so that the
-    // two dependent DRAM round trips at the head of a triple (index -> records / targets) are hidden behind the previous one
+    // a warp starts with triple number (its own index) and then takes tickets from a global counter (a triple replays 0 .. R-1
+    // actions per sample, so equal COUNTS of triples per warp leave the last wave of a launch a fifth full): the index of
+    // the NEXT triple is read while this one is processed, and its records and target rows are pulled into L2 before the
+    // slots of this one are built, so that the two dependent DRAM round trips at the head of a triple (index -> records /
+    // targets) are hidden behind the previous one
     const long long nwarps = (long long)gridDim.x * WARPS, ntrip = (nb + SPW - 1) / SPW;
     long long trip = (long long)blockIdx.x * WARPS + warp;
     if (trip >= ntrip) return;
@@ -518,7 +522,9 @@ __global__ void __launch_bounds__(32 * WARPS, 4)
     for (;;) {
     const long long b0 = trip * SPW;
     const int ns = (int)min((long long)SPW, nb - b0);
-    const long long ntr = trip + nwarps;
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1ULL);
+    const long long ntr = nwarps + (long long)__shfl_sync(0xFFFFFFFFu, tk, 0);
     long long nid = -1;
     if (ntr < ntrip && lane < (int)min((long long)SPW, nb - ntr * SPW)) nid = idx[ntr * SPW + lane];
     // ---- the warp's samples: lane q < ns holds sample q; everybody gets (demo, a) of every sample by shuffle
@@ -950,6 +956,32 @@ static int launch_demo_sample_dm(const uint8_t *tape_dm, const uint8_t *targets,
 
 } // namespace tg
 
+namespace tg {
+// Work counters of the persistent batcher: static device memory (the library allocates nothing), one slot per launch, handed
+// out round robin per device.  A slot is zeroed on the launch's stream right before the kernel; its event (recorded after
+// the kernel) keeps a later launch that comes round to the same slot from zeroing it while the earlier one still runs.
+constexpr int TICKET_SLOTS = 64, TICKET_MAXDEV = 64;
+__device__ unsigned long long g_tickets[TICKET_SLOTS];
+static cudaEvent_t g_ticket_done[TICKET_MAXDEV][TICKET_SLOTS];
+static unsigned g_ticket_next[TICKET_MAXDEV];
+static std::mutex g_ticket_mu;
+static int ticket_acquire(cudaStream_t st, unsigned long long **ticket, cudaEvent_t *done) {
+    int dev = 0;
+    TG_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= TICKET_MAXDEV) return TG_E_ARG;
+    unsigned long long *base = nullptr;
+    TG_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&base), g_tickets));
+    std::lock_guard<std::mutex> lock(g_ticket_mu);
+    const int slot = (int)(g_ticket_next[dev]++ % TICKET_SLOTS);
+    cudaEvent_t &ev = g_ticket_done[dev][slot];
+    if (!ev) TG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    else TG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    TG_CUDA(cudaMemsetAsync(base + slot, 0, sizeof(unsigned long long), st));
+    *ticket = base + slot, *done = ev;
+    return TG_OK;
+}
+} // namespace tg
+
 extern "C" {
 
 int tg_demo_sample(const uint8_t *tape, int64_t tape_step_stride, const int8_t *slab, int64_t N, int R, int S, int dim_t,
@@ -991,18 +1023,23 @@ int tg_demo_sample_dm(const uint8_t *tape_dm, const void *targets, int targets_i
         const long long per_cta = (long long)tg::rows9::WARPS * tg::rows9::SPW;
         const long long want = (nb + per_cta - 1) / per_cta;
         const unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4); // persistent warps: four CTAs per SM
+        unsigned long long *ticket = nullptr;
+        cudaEvent_t done = nullptr;
+        const int trc = tg::ticket_acquire(st, &ticket, &done);
+        if (trc != TG_OK) return trc;
         if (targets_i16) {
             auto kern = tg::rows9::demo_sample_rows9_kernel<true, true>;
             TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             kern<<<grid, 32 * tg::rows9::WARPS, smem, st>>>(tape_dm, (const uint8_t *)targets, N, R, dim_t, replay_shift, (const long long *)idx,
-                                                            nb, states, scalars, (long long *)actions, rewards);
+                                                            nb, states, scalars, (long long *)actions, rewards, ticket);
         } else {
             auto kern = tg::rows9::demo_sample_rows9_kernel<false, true>;
             TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             kern<<<grid, 32 * tg::rows9::WARPS, smem, st>>>(tape_dm, (const uint8_t *)targets, N, R, dim_t, replay_shift, (const long long *)idx,
-                                                            nb, states, scalars, (long long *)actions, rewards);
+                                                            nb, states, scalars, (long long *)actions, rewards, ticket);
         }
         TG_CUDA(cudaGetLastError());
+        TG_CUDA(cudaEventRecord(done, st));
         return TG_OK;
     }
     TG_SWITCH_S(S, {

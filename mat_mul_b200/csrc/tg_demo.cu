@@ -234,7 +234,8 @@ struct DemoCfg {
         return pass * pass_stride(R) + (g - pass * GPASS) * PITCH;
     }
     // regions, per-demo flags, work counter + 2 retry-list counters, 2 retry lists of NT entries
-    static __host__ __device__ constexpr int smem_bytes(int R) { return main_bytes(R) + TG * 4 + 16 + 2 * NT * 4; }
+    static constexpr int FLAG_BYTES = ((TG + 3) & ~3) * 4; // per-demo flags, rounded so that what follows stays 16-byte aligned
+    static __host__ __device__ constexpr int smem_bytes(int R) { return main_bytes(R) + FLAG_BYTES + 16 + 2 * NT * 4; }
 };
 
 // "is this factor all zero" over packed token words: OR of (word ^ zero_pat) under the factor's byte mask
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(NT, S == 16 ? (NT <= 128 ? 4 : 2) : (S == 9 ? 
     uint8_t *s_rec = smem;
     constexpr int MMA_SCRATCH = MMA > 0 ? (NT / 32) * acc16::WARP_WORDS * 4 : 0; // per-warp H and U2 tables
     uint32_t *s_flag = reinterpret_cast<uint32_t *>(smem + (MMA == 0 ? C::main_bytes(R) : MMA > 0 ? C::rec_region(R) + MMA_SCRATCH : 0)); // [TG]
-    uint32_t *s_work = s_flag + C::TG;   // [0] next fresh pair, [1], [2] sizes of the two retry lists
+    uint32_t *s_work = s_flag + C::FLAG_BYTES / 4; // [0] next fresh pair, [1], [2] sizes of the two retry lists
     uint32_t *s_list = s_work + 4;       // [2][NT]  pending (pair | try << 16); ALIAS: the tables live here instead
     uint32_t *s_alias = MMA > 0 ? reinterpret_cast<uint32_t *>(smem + C::rec_region(R)) : s_list; // fused kernels: the (not yet used) MMA scratch
 
@@ -793,7 +794,7 @@ template <int NTHR, int NT, int NPASS, int MMA>
 static int launch_demo16_mma(unsigned long long first, long long N, int R, int shift, const Categorical &cat, int max_tries,
                              uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     using C = DemoCfg<16, NT, NPASS>;
-    const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : 0) + C::TG * 4 + 16 + 2 * NT * 4;
+    const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : 0) + C::FLAG_BYTES + 16 + 2 * NT * 4;
     if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
     const long long grid = (N + C::TG - 1) / C::TG;
@@ -813,7 +814,7 @@ static int launch_demo_alias(unsigned long long first, long long N, int R, int s
     using C = DemoCfg<S, NT, NPASS>;
     constexpr int TAIL = MMA > 0 ? 2 * NT * 4 : (2 * NT * 4 > AliasGeo<S>::SMEM_BYTES ? 2 * NT * 4 : AliasGeo<S>::SMEM_BYTES);
     static_assert(MMA <= 0 || AliasGeo<S>::SMEM_BYTES <= acc16::WARP_WORDS * 4, "the alias tables overlay one warp's MMA scratch");
-    const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : C::main_bytes(R)) + C::TG * 4 + 16 + TAIL;
+    const int smem = (MMA > 0 ? C::rec_region(R) + (NT / 32) * acc16::WARP_WORDS * 4 : C::main_bytes(R)) + C::FLAG_BYTES + 16 + TAIL;
     if (smem > 227 * 1024 || R > 65535 || (long long)C::TG * R >= (1LL << 16)) return TG_E_ARG;
     const uint32_t magic = R == 1 ? 0u : (uint32_t)((0x100000000ULL + (unsigned)R - 1) / (unsigned)R);
     const long long grid = (N + C::TG - 1) / C::TG;
