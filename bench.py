@@ -444,8 +444,15 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
     idx = torch.randint(0, B * R, (1 << 16,), device=dev)
     store = env.DemoStore.from_tape(tape3, slab, S, shift)  # demo-major action records next to the step-major tape
     ms = _time_ms(lambda: store.samples(idx, 2, replay_shift=shift), 10, torch)
-    out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2,
+    out["demo_sample"] = {"value": idx.numel() / ms * 1e3, "unit": "samples/s", "ms": ms, "dim_t": 2, "samples": idx.numel(),
                           "hbm_frac": idx.numel() * (2 * S ** 3 * 4) / (ms * 1e-3) / 1e9 / peak}
+    # the same batcher on a batch four times as large (the tail of the persistent grid weighs less) and with four state slots
+    idx4 = torch.randint(0, B * R, (1 << 18,), device=dev)
+    for key, ii, T in (("batch_2e18", idx4, 2), ("dim_t_4", idx, 4)):
+        ms = _time_ms(lambda: store.samples(ii, T, replay_shift=shift), 5, torch)
+        out["demo_sample"][key] = {"value": ii.numel() / ms * 1e3, "ms": ms, "dim_t": T, "samples": ii.numel(),
+                                   "hbm_frac": ii.numel() * (T * S ** 3 * 4) / (ms * 1e-3) / 1e9 / peak}
+    del idx4
     del store
     # batched leaf expansion (K8): k = 8 candidate actions per state, children + flags + nnz (+ keys)
     nbp = min(B, 1 << 17)

@@ -6,13 +6,14 @@ import torch
 from mat_mul_b200 import env
 V5, P5 = (-2, -1, 0, 1, 2), (0.05, 0.10, 0.70, 0.10, 0.05)
 which = sys.argv[1]
-if which == "sample":
-    S, R, N = 9, 23, 1 << 18
-    tape, slab, _ = env.make_synthetic_demos(N, R, S, V5, P5, 2, seed=1)
-    store = env.DemoStore.from_tape(tape, slab, S, 2)
-    idx = torch.randint(0, N * R, (1 << 16,), device="cuda")
+if which in ("sample", "sample4"):
+    S, R, N = (9, 23, 1 << 18) if which == "sample" else (4, 7, 1 << 20)
+    vals, probs, shift = (V5, P5, 2) if S == 9 else ((-1, 0, 1), (0.15, 0.7, 0.15), 1)
+    tape, slab, _ = env.make_synthetic_demos(N, R, S, vals, probs, shift, seed=1)
+    store = env.DemoStore.from_tape(tape, slab, S, shift)
+    idx = torch.randint(0, N * R, (1 << (16 if S == 9 else 18),), device="cuda")
     for _ in range(3):
-        store.samples(idx, 2, replay_shift=2)
+        store.samples(idx, 2, replay_shift=shift)
 elif which.startswith("basis"):
     S = int(which[5:])
     R, N = {4: (7, 1 << 20), 9: (23, 1 << 18), 16: (49, 1 << 17)}[S]
