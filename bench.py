@@ -478,6 +478,8 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
         ms_step = _time_ms(lambda: env.step_batch(s4, t4[R4 - 1], S4, 1, out=o4, flags=f4, nnz=n4), 10, torch)
         out["size_4x4x4"] = {"games": B4, "env_steps_per_sec": B4 / ms_step * 1e3, "step_ms": ms_step,
                              "step_hbm_frac": B4 * STEP_BYTES[4] / (ms_step * 1e-3) / 1e9 / peak}
+        # change of basis at 4x4x4: one thread per game, exact int32 in registers (csrc/tg_basis.cu basis4_thread_kernel)
+        out["size_4x4x4"]["change_of_basis"], _ = basis_block(S4, s4, 1 << 20, 0.3)
         del t4, s4, o4
         # BASELINE.json configs[2]: 16x16x16 demos (rank <= 49) followed by the change-of-basis augmentation, one
         # (A, B, C) triple per demo -- the one contraction that runs on the tensor cores (csrc/tg_basis_mma.cu)

@@ -30,7 +30,7 @@ for S, R, N, vals, probs, shift in [(4, 7, 1 << 22, (-1, 0, 1), (0.15, 0.7, 0.15
         for T in (2, 4):
             ms = t_ms(lambda: store.samples(idx, T, replay_shift=shift))
             print(f"S={S} demo_sample nb={nb} T={T}: {ms:.3f} ms {nb / ms / 1e6:.4f} G samples/s hbm_frac={nb * T * S**3 * 4 / ms / 1e6 / PEAK:.3f}")
-    nbg = min(N, 1 << 18)
+    nbg = min(N, 1 << 18 if S == 9 else 1 << 20)
     mats = env.sample_unimodular(nbg, S, seed=3, p_nonzero=0.3)
     for dt in (torch.int16, torch.int8):
         out = torch.empty((nbg, lay.game_pitch), dtype=dt, device="cuda")

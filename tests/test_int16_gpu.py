@@ -81,7 +81,8 @@ def test_change_of_basis_int16_extreme_inputs(env, S):
     fits = (np.abs(want.reshape(N, -1) + 0.5) < 32768).all(1)
     assert not (f & 0x80).any()
     assert np.array_equal((f & 4) == 0, fits)
-    assert fits.sum() > N // 2 and stats["exact_int32_redo"] > 0
+    # 4x4x4 runs one thread per game in exact int32 from the start: nothing is left to redo there
+    assert fits.sum() > N // 2 and (stats["exact_int32_redo"] > 0 or S == 4)
     assert np.array_equal(slab16_to_dense(out16.cpu().numpy(), S)[fits], want[fits])
 
 
