@@ -733,6 +733,132 @@ __global__ void __launch_bounds__(32 * WARPS, 4)
 }
 } // namespace rows9
 
+// ------------------------------------------------------------------ K4 at 4x4x4: one thread per (sample, row i)
+// A 4x4x4 sample is tiny (64-byte target, <= R 16-byte records, dim_t * 256 bytes out): the word-column kernel above spends
+// 165 warp-instructions per sample in staging loops and CTA barriers (0.15-0.28 of HBM).  Here four threads own the four
+// rows of a sample entirely in registers -- 16 int32 entries, exact for any target bound, no shared memory, no barrier: the
+// target row is one 16-byte load, every record one 16-byte load (the four threads of a sample read the same one), a
+// replayed action whose u_i is zero is skipped, and a state row leaves as four 16-byte stores; the four threads of a
+// sample write 256 contiguous bytes per slot.
+namespace rows4 {
+template <bool TGT16>
+__global__ void __launch_bounds__(128)
+    demo_sample_rows4_kernel(const uint8_t *__restrict__ tape_dm, const uint8_t *__restrict__ targets, long long N, int R, int dim_t,
+                             int replay_shift, const long long *__restrict__ idx, long long nb, float *__restrict__ states,
+                             float *__restrict__ scalars, long long *__restrict__ actions, float *__restrict__ rewards) {
+    const long long gt = (long long)blockIdx.x * 128 + threadIdx.x;
+    const long long b = gt >> 2;
+    const int i = (int)(gt & 3);
+    if (b >= nb) return;
+    const long long id = idx[b];
+    long long demo = -1;
+    int a = 0;
+    if (id >= 0) split_index(id, R, demo, a);
+    float *st = states + b * (long long)dim_t * 64 + i * 16; // row i of slot 0
+    const bool aligned = (reinterpret_cast<uintptr_t>(states) & 15) == 0; // then every row of every sample is 16-byte aligned
+    auto put_row = [&](float *row, const float (&f)[16]) {
+        if (aligned) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) st_f32x4(row + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) store_run<4>(row + 4 * j, 4, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+    };
+    const float zeros[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (demo < 0 || demo >= N) { // bad index: zero states, nothing else written (as the column kernel)
+        for (int s = 0; s < dim_t; s++) put_row(st + (size_t)s * 64, zeros);
+        return;
+    }
+    // ---- head = target - sum of the later actions
+    int acc[16];
+    if constexpr (TGT16) {
+        const uint4 *tp = reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(targets) + demo * 64 + i * 16);
+        const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[2 * e] = (int)(short)(tw[e] & 0xFFFFu), acc[2 * e + 1] = (int)tw[e] >> 16;
+    } else {
+        const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(targets + demo * 64 + i * 16));
+        const uint32_t tw[4] = {t0.x, t0.y, t0.z, t0.w};
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc[e] = (int)(int8_t)(tw[e >> 2] >> (8 * (e & 3)));
+    }
+    const uint4 *rec = reinterpret_cast<const uint4 *>(tape_dm + (size_t)demo * R * 16); // record j: x = u, y = v, z = w tokens
+    const int ush = 8 * i;
+    const uint32_t sh4 = (uint32_t)replay_shift * ONES4;
+    auto replay = [&](const uint4 &q) { // acc -= u_i * v (x) w of one record
+        // tokens -> int8 coefficients, four at a time (no borrow between bytes: token | 0x80 > shift), then one sign-
+        // extending PRMT per coefficient
+        const uint32_t cv = ((q.y | H4) - sh4) ^ H4, cw = ((q.z | H4) - sh4) ^ H4;
+        const int nui = replay_shift - (int)((q.x >> ush) & 0xFFu);
+        const int w[4] = {sext_byte<0>(cw), sext_byte<1>(cw), sext_byte<2>(cw), sext_byte<3>(cw)};
+        const int v[4] = {sext_byte<0>(cv), sext_byte<1>(cv), sext_byte<2>(cv), sext_byte<3>(cv)};
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int c = nui * v[jj];
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[4 * jj + k] += c * w[k];
+        }
+    };
+    constexpr int RMAX = 8;
+    uint4 qa; // the sample's own action
+    if (R <= RMAX) {
+        // every record of the demo in flight at once (the loads do not wait for each other, nor for the target row)
+        uint4 q[RMAX];
+#pragma unroll
+        for (int j = 0; j < RMAX; j++) q[j] = (j < R && j >= a) ? __ldg(rec + j) : make_uint4(0, 0, 0, 0);
+        qa = q[0];
+#pragma unroll
+        for (int j = 1; j < RMAX; j++) {
+            if (j == a) qa = q[j];
+            if (j > a && j < R) replay(q[j]);
+        }
+    } else {
+        qa = __ldg(rec + a);
+#pragma unroll 2
+        for (int j = a + 1; j < R; j++) replay(__ldg(rec + j));
+    }
+    {
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) f[e] = (float)acc[e];
+        put_row(st, f);
+    }
+    // ---- history slots: rank-1 tensors of the next actions, latest first
+    const int hi = min(a + dim_t, R);
+    for (int s = 1; s < dim_t; s++) {
+        const int j = hi - s;
+        float *row = st + (size_t)s * 64;
+        if (j >= a + 1) {
+            const uint4 q = __ldg(rec + j);
+            const int ui = (int)((q.x >> ush) & 0xFFu) - replay_shift;
+            float f[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int c = ui * ((int)((q.y >> (8 * jj)) & 0xFFu) - replay_shift);
+#pragma unroll
+                for (int k = 0; k < 4; k++) f[4 * jj + k] = (float)(c * ((int)((q.z >> (8 * k)) & 0xFFu) - replay_shift));
+            }
+            put_row(row, f);
+        } else {
+            put_row(row, zeros);
+        }
+    }
+    if (i == 0) {
+        scalars[b] = (float)(R - a);
+        rewards[b] = -(float)(a + 1);
+    }
+    // the sample's own action: raw tokens; thread i writes tokens 3i .. 3i+2
+#pragma unroll
+    for (int x = 0; x < 3; x++) {
+        const int qi = 3 * i + x;
+        const uint32_t word = qi < 4 ? qa.x : (qi < 8 ? qa.y : qa.z);
+        actions[b * 12 + qi] = (long long)((word >> (8 * (qi & 3))) & 0xFFu);
+    }
+}
+} // namespace rows4
+
 // step-major tape [R][N][TP] -> demo-major records [N][R][TP], 16 bytes per thread
 __global__ void tape_to_demo_major_kernel(const uint4 *__restrict__ src, long long src_step_stride16, uint4 *__restrict__ dst,
                                           long long N, int R, int tp16) {
@@ -1040,6 +1166,18 @@ int tg_demo_sample_dm(const uint8_t *tape_dm, const void *targets, int targets_i
         }
         TG_CUDA(cudaGetLastError());
         TG_CUDA(cudaEventRecord(done, st));
+        return TG_OK;
+    }
+    if (S == 4) { // one thread per (sample, row), exact int32 (any target bound)
+        const long long threads = nb * 4;
+        const unsigned grid = (unsigned)((threads + 127) / 128);
+        if (targets_i16)
+            tg::rows4::demo_sample_rows4_kernel<true><<<grid, 128, 0, st>>>(tape_dm, (const uint8_t *)targets, N, R, dim_t, replay_shift,
+                                                                         (const long long *)idx, nb, states, scalars, (long long *)actions, rewards);
+        else
+            tg::rows4::demo_sample_rows4_kernel<false><<<grid, 128, 0, st>>>(tape_dm, (const uint8_t *)targets, N, R, dim_t, replay_shift,
+                                                                          (const long long *)idx, nb, states, scalars, (long long *)actions, rewards);
+        TG_CUDA(cudaGetLastError());
         return TG_OK;
     }
     TG_SWITCH_S(S, {
