@@ -9,8 +9,9 @@
 // with per-child flags (terminal / null action / range), non-zero count and 64-bit state key.
 //
 // The parent is read ONCE: thread (parent, word column) keeps its S row words in registers and produces the k
-// children one after the other into a two-stage shared-memory tile; each child game leaves with a TMA bulk store
-// while the next one is computed.  HBM traffic per child: GP * (1 + 1/k) + TP + 13 bytes.
+// children one after the other into a three-stage shared-memory tile; each child game leaves with a TMA bulk store
+// while the next ones are computed (three stages so that ONE CTA barrier per child is enough: a stage is rewritten two
+// barriers after the threads that issued its stores have seen them drain).  HBM traffic per child: GP * (1 + 1/k) + TP + 13 bytes.
 // The state key is the trilinear form of the state at three fixed 64-bit vectors (sum T[i][j][k] A_i B_j C_k mod 2^64,
 // tg_state_key), so a child's key is the parent's key (hashed once per parent) minus
 // (sum u_i A_i)(sum v_j B_j)(sum w_k C_k): 3 S multiply-adds on the action's tokens, done for all TG * k children of the
@@ -26,9 +27,10 @@ struct ExpCfg {
     static constexpr int ACTIVE = TG * G::WR;
     static constexpr int STAGE_BYTES = TG * G::GP;
     static __host__ __device__ constexpr int tok_bytes(int k) { return (TG * k * G::TP + 15) & ~15; }
-    // tokens, 2 child stages, per-(stage, game) partial word and key
+    static constexpr int NSTAGE = 3;
+    // tokens, NSTAGE child stages, per-(stage, game) partial word and key
     static __host__ __device__ constexpr int smem_bytes(int k) {
-        return tok_bytes(k) + 2 * STAGE_BYTES + 2 * TG * 4 + TG * 8 + 16 + NT * 8;
+        return tok_bytes(k) + NSTAGE * STAGE_BYTES + ((NSTAGE * TG * 4 + 7) & ~7) + TG * 8 + 16 + NT * 8;
     }
 };
 
@@ -50,9 +52,10 @@ __global__ void __launch_bounds__(NT)
     using G = Geo<S>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_tok = smem;                                                            // [TG][k][TP]
-    uint8_t *s_out = smem + C::tok_bytes(k);                                          // [2][TG][GP]
-    uint32_t *s_part = reinterpret_cast<uint32_t *>(s_out + 2 * C::STAGE_BYTES);      // [2][TG]
-    unsigned long long *s_pkey = reinterpret_cast<unsigned long long *>(s_part + 2 * C::TG); // [TG] parent keys
+    constexpr int NSTAGE = C::NSTAGE;
+    uint8_t *s_out = smem + C::tok_bytes(k);                                          // [NSTAGE][TG][GP]
+    uint32_t *s_part = reinterpret_cast<uint32_t *>(s_out + NSTAGE * C::STAGE_BYTES); // [NSTAGE][TG]
+    unsigned long long *s_pkey = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(s_part) + ((NSTAGE * C::TG * 4 + 7) & ~7)); // [TG] parent keys
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_pkey + C::TG);
     unsigned long long *s_ph = reinterpret_cast<unsigned long long *>(s_bar + 2); // [NT] parent key, per word column
 
@@ -68,9 +71,9 @@ __global__ void __launch_bounds__(NT)
         mbar_init(s_bar, 1);
         mbar_fence_init();
     }
-    // game padding of both child stages is zero and stays zero (threads only write their word columns of the S rows)
-    for (int w = tid; w < 2 * C::STAGE_BYTES / 4; w += NT) reinterpret_cast<uint32_t *>(s_out)[w] = 0;
-    for (int i = tid; i < 2 * C::TG; i += NT) s_part[i] = 0;
+    // game padding of the child stages is zero and stays zero (threads only write their word columns of the S rows)
+    for (int w = tid; w < NSTAGE * C::STAGE_BYTES / 4; w += NT) reinterpret_cast<uint32_t *>(s_out)[w] = 0;
+    for (int i = tid; i < NSTAGE * C::TG; i += NT) s_part[i] = 0;
     // key constants of this thread's word column: B_j C_k of its four entries (0 in the row padding)
     unsigned long long kb[4] = {0, 0, 0, 0};
     if constexpr (KEYS) {
@@ -135,10 +138,10 @@ __global__ void __launch_bounds__(NT)
         }
     }
 
-    for (int c = 0; c < k; c++) {
-        const int st = c & 1;
+    for (int c = 0, st = 0; c < k; c++, st = st + 1 == NSTAGE ? 0 : st + 1) {
         uint8_t *stage = s_out + st * C::STAGE_BYTES;
-        // the bulk stores of child c-2 have finished reading this stage (issuing threads waited, then the barrier below)
+        // the bulk stores of child c-3 have finished reading this stage: the threads that issued them waited for child c-2's
+        // predecessor to drain (bulk_wait_read<1> below, iteration c-2) before they arrived at the barrier of iteration c-1
         if (active) {
             const uint8_t *tok = s_tok + ((size_t)g * k + c) * G::TP;
             const int32_t vw = pack_vw<S>(tok, L, shift);
@@ -170,11 +173,9 @@ __global__ void __launch_bounds__(NT)
             flags[child] = (uint8_t)partial_flags(sum);
             nnz[child] = (int32_t)(sum & 0xFFFFu);
             s_part[st * C::TG + tid] = 0;
-            bulk_wait_read<1>(); // the store of child c-1 (other stage) has drained: safe to overwrite next iteration
+            bulk_wait_read<1>(); // the store of child c-1 has drained; its stage is rewritten at c+2, one barrier from here
         }
-        // (the barrier at the end of the NEXT iteration's compute orders "stage drained" before its reuse at c+2;
-        //  the one here orders the reset of s_part before the next child's atomics)
-        __syncthreads();
+        // no second barrier: the partial words of this stage are reset here and next touched at child c+3, two barriers away
     }
     if (tid < ng) bulk_wait<0>();
 }
