@@ -212,8 +212,8 @@ extern "C" int tg_expand_children(const int8_t *parents, const uint8_t *tape, in
     cudaStream_t st = (cudaStream_t)stream;
     switch (S) {
     case 4: return tg::launch_expand<4, 256>(parents, tape, k, children, flags, nnz, (unsigned long long *)keys, B, shift, st);
-    case 9: return tg::launch_expand<9, 256>(parents, tape, k, children, flags, nnz, (unsigned long long *)keys, B, shift, st);
-    case 16: return tg::launch_expand<16, 256>(parents, tape, k, children, flags, nnz, (unsigned long long *)keys, B, shift, st);
+    case 9: return tg::launch_expand<9, 128>(parents, tape, k, children, flags, nnz, (unsigned long long *)keys, B, shift, st);
+    case 16: return tg::launch_expand<16, 128>(parents, tape, k, children, flags, nnz, (unsigned long long *)keys, B, shift, st);
     }
     return TG_E_ARG;
 }
