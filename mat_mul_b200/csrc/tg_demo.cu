@@ -1179,6 +1179,10 @@ int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N,
     if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R))
         return tg::launch_demo_acc16_mma(tape, tape_step_stride, N, R, shift, slab, flags, 0, (cudaStream_t)stream);
     tg::Categorical cat = {};
+    // 9x9x9: walk only the terms with a non-zero v_j (the masks are built from the tape itself, so this is exact for any tape;
+    // with the reference's distributions 70 % of the coefficients are zero: 0.62 -> 0.55 ms per 2^20 demos; a tape without zeros
+    // pays ~15 % in the term loop)
+    cat.sparse_terms = S == 9 ? 1u : 0u;
     return tg::dispatch_demo<false, 2>(0, N, R, S, shift, cat, 1, const_cast<uint8_t *>(tape), tape_step_stride, slab, flags,
                                        (cudaStream_t)stream);
 }
