@@ -164,6 +164,36 @@ def test_change_of_basis_shared_triple_and_identity(env):
     assert torch.equal(back, slab)
 
 
+@pytest.mark.parametrize("off", [0, 1, 4, 8])
+def test_change_of_basis_4_matrices_at_any_alignment_and_shared(env, off):
+    # 4x4x4 runs one thread per game with 16-byte matrix loads; matrices that are not 16-byte aligned (a view into a larger
+    # buffer) and the shared triple take other routes -- all of them equal the int64 einsum, int8 and int16 out
+    S, N = 4, 777
+    rng = np.random.default_rng(40 + off)
+    T = rng.integers(-128, 128, (N, S, S, S)) * (rng.random((N, S, S, S)) < 0.6)
+    m = rng.integers(-2, 3, (N, 3, S, S))
+    want = np.einsum("nia,njb,nkc,nabc->nijk", m[:, 0], m[:, 1], m[:, 2], T.astype(np.int64))
+    slab = torch.from_numpy(dense_to_slab(T)).cuda()
+    buf = torch.zeros(N * 3 * S * S + 64, dtype=torch.int8, device="cuda")
+    base = (-buf.data_ptr()) % 16 + off  # byte offset `off` from a 16-byte boundary
+    mats = buf[base:base + N * 3 * S * S].view(N, 3, S, S)
+    mats.copy_(torch.from_numpy(m.astype(np.int8)))
+    assert mats.data_ptr() % 16 == off
+    out16, f16 = env.change_of_basis(slab, mats, S, out_dtype=torch.int16)
+    fits16 = (np.abs(want.reshape(N, -1) + 0.5) < 32768).all(1)
+    assert np.array_equal((f16.cpu().numpy() & 4) == 0, fits16)
+    from tests.test_int16_gpu import slab16_to_dense
+    assert np.array_equal(slab16_to_dense(out16.cpu().numpy(), S)[fits16], want[fits16])
+    out8, f8 = env.change_of_basis(slab, mats, S)
+    zone = (np.abs(want.reshape(N, -1) + 0.5) < 64).all(1)
+    assert np.array_equal((f8.cpu().numpy() & 4) == 0, zone)
+    assert np.array_equal(slab_to_dense(out8.cpu().numpy(), S)[zone], want[zone])
+    shared, fs = env.change_of_basis(slab, mats[5:6].contiguous(), S, out_dtype=torch.int16)
+    want_s = np.einsum("ia,jb,kc,nabc->nijk", m[5, 0], m[5, 1], m[5, 2], T.astype(np.int64))
+    ok = (np.abs(want_s.reshape(N, -1) + 0.5) < 32768).all(1)
+    assert np.array_equal(slab16_to_dense(shared.cpu().numpy(), S)[ok], want_s[ok])
+
+
 @pytest.mark.parametrize("S,amp,dens", [(4, 3, 1.0), (9, 3, 0.6), (9, 1, 0.2), (16, 2, 0.5), (16, 7, 1.0)])
 def test_change_of_basis_large_matrices_take_the_exact_path(env, S, amp, dens):
     # dense / large matrices overflow the packed lanes of the fast kernel: those games are redone by the exact
