@@ -480,6 +480,12 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
                              "step_hbm_frac": B4 * STEP_BYTES[4] / (ms_step * 1e-3) / 1e9 / peak}
         # change of basis at 4x4x4: one thread per game, exact int32 in registers (csrc/tg_basis.cu basis4_thread_kernel)
         out["size_4x4x4"]["change_of_basis"], _ = basis_block(S4, s4, 1 << 20, 0.3)
+        # fused rollout at 4x4x4: one thread per game, the game in registers for all K steps
+        rev4 = t4.flip(0).contiguous()
+        ms_r4 = _time_ms(lambda: env.rollout(s4, rev4, S4, 1, out=o4), 5, torch)
+        out["size_4x4x4"]["rollout"] = {"value": B4 * R4 / ms_r4 * 1e3, "unit": "game-steps/s", "K": R4, "ms": ms_r4,
+                                        "hbm_frac": B4 * (2 * S4 ** 3 + R4 * 3 * S4 + 8) / (ms_r4 * 1e-3) / 1e9 / peak}
+        del rev4
         # sample batcher at 4x4x4 (the reference's default size): four threads per sample, rows in registers
         st4 = env.DemoStore.from_tape(t4, s4, S4, 1)
         i4 = torch.randint(0, B4 * R4, (1 << 20,), device=dev)

@@ -24,6 +24,15 @@
 
 namespace tg {
 
+// sign-extended byte B of a word of int8 coefficients
+template <int B>
+__device__ __forceinline__ int sext_byte4(uint32_t w) {
+    constexpr uint32_t sel = (uint32_t)B | ((uint32_t)(B | 8) << 4) | ((uint32_t)(B | 8) << 8) | ((uint32_t)(B | 8) << 12);
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "r"(sel));
+    return (int)d;
+}
+
 template <int S, int NT, int NST>
 struct RollCfg {
     using G = Geo<S>;
@@ -208,6 +217,93 @@ __global__ void __launch_bounds__(NT + 32)
     }
 }
 
+// ------------------------------------------------------------------ 4x4x4: one THREAD per game
+// A 4x4x4 game is 16 words: it lives in the registers of one thread for all K steps (offset-binary, tg_step.cuh).  A step is
+// one 16-byte load of the game's record (coalesced: consecutive threads, consecutive records of the step-major tape), the
+// twelve coefficients with three packed subtractions and eight sign-extending PRMTs, sixteen products u_i v_j and sixteen
+// IMADs with the integer form of pack(w): ~80 instructions per game-step and THREAD (2.5 per warp and game-step against
+// ~12 for the word-column kernel), no shared memory, no barrier, "solved" is a register test.  Same contract as
+// rollout_kernel (freeze at the zero tensor, steps, nnz, TERMINAL / RANGE flags, token bound).
+template <bool FREEZE>
+__global__ void __launch_bounds__(128)
+    rollout4_thread_kernel(const int8_t *__restrict__ slab_in, const uint8_t *__restrict__ tape, long long tape_step_stride, int K,
+                           int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, int32_t *__restrict__ nnz,
+                           int32_t *__restrict__ steps, long long B, int shift, int chk) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= B) return;
+    uint32_t row[16]; // word 4 i + j = entries (i, j, 0..3)
+    uint32_t bad = 0, nzw = 0;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(slab_in + n * 64);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 t = __ldg(src + i);
+            row[4 * i] = t.x, row[4 * i + 1] = t.y, row[4 * i + 2] = t.z, row[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            nzw |= row[e];
+            row[e] ^= H4;
+            bad |= ~(row[e] ^ (row[e] << 1)); // the start state must already be inside [-64,63]
+        }
+    }
+    bool alive = !FREEZE || nzw != 0;
+    int until = chk, my_steps = 0;
+    const uint32_t sh4 = (uint32_t)shift * ONES4, tokmax = (uint32_t)(0x7F - 2 * shift) * ONES4;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(tape + n * 16);
+    const long long stride16 = tape_step_stride / 16;
+    uint4 q = K > 0 ? __ldg(rec) : make_uint4(0, 0, 0, 0);
+    for (int t = 0; t < K; t++) {
+        const uint4 cur = q;
+        if (t + 1 < K) q = __ldg(rec + (long long)(t + 1) * stride16); // next step's record in flight
+        if (!alive) {
+            if (FREEZE) break; // frozen at the zero tensor: nothing left to do for this game
+            continue;
+        }
+        // tape contract (tg_step.cuh): every token <= 2 * shift, else the packed update may have aliased
+        const uint32_t over = ((((cur.x & 0x7F7F7F7Fu) + tokmax) | cur.x) | (((cur.y & 0x7F7F7F7Fu) + tokmax) | cur.y) |
+                               (((cur.z & 0x7F7F7F7Fu) + tokmax) | cur.z)) & H4;
+        if (over) bad = 0xFFFFFFFFu;
+        const uint32_t cu = ((cur.x | H4) - sh4) ^ H4, cv = ((cur.y | H4) - sh4) ^ H4; // int8 coefficients
+        const int wi = (int)(cur.z - sh4);                                             // integer form of pack(w)
+        const int u[4] = {sext_byte4<0>(cu), sext_byte4<1>(cu), sext_byte4<2>(cu), sext_byte4<3>(cu)};
+        const int v[4] = {sext_byte4<0>(cv), sext_byte4<1>(cv), sext_byte4<2>(cv), sext_byte4<3>(cv)};
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                row[4 * i + j] -= (uint32_t)(u[i] * v[j] * wi);
+                sum += row[4 * i + j];
+            }
+        if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
+            until = chk;
+#pragma unroll
+            for (int e = 0; e < 16; e++) bad |= ~(row[e] ^ (row[e] << 1));
+        }
+        my_steps = t + 1;
+        if (FREEZE && sum == (uint32_t)(16ull * H4)) { // checksum of the zero tensor: confirm word by word
+            bool zero = true;
+#pragma unroll
+            for (int e = 0; e < 16; e++) zero = zero && row[e] == H4;
+            if (zero) alive = false;
+        }
+    }
+    uint32_t cnt = 0;
+    uint4 *dst = reinterpret_cast<uint4 *>(slab_out + n * 64);
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        bad |= ~(row[e] ^ (row[e] << 1));
+        row[e] ^= H4;
+        cnt += (uint32_t)__popc(nonzero_mask(row[e]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[i] = make_uint4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+    flags[n] = (uint8_t)((cnt == 0 ? TG_FLAG_TERMINAL : 0u) | ((bad & H4) != 0 ? TG_FLAG_RANGE : 0u));
+    nnz[n] = (int32_t)cnt;
+    if (steps) steps[n] = my_steps;
+}
+
 template <int S, int NT, int NST>
 static int launch_rollout(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out,
                           uint8_t *flags, int32_t *nnz, int32_t *steps, long long B, int shift, int freeze, cudaStream_t st) {
@@ -233,7 +329,20 @@ static int rollout_dispatch(const int8_t *slab_in, const uint8_t *tape, int64_t 
     if (((uintptr_t)slab_in | (uintptr_t)slab_out | (uintptr_t)tape | (uintptr_t)tape_step_stride) & 15) return TG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     switch (S) {
-    case 4: return tg::launch_rollout<4, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+    case 4: {
+#ifdef TG_TUNING
+        if (tg::tuning_env("TG_ROLLOUT_COLUMNS", 0)) // A/B: the word-column kernel
+            return tg::launch_rollout<4, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+#endif
+        const int s3 = shift * shift * shift;
+        const int chk = s3 >= 64 ? 1 : 64 / s3;
+        const long long grid = (B + 127) / 128;
+        if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+        if (freeze) tg::rollout4_thread_kernel<true><<<(int)grid, 128, 0, st>>>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, chk);
+        else tg::rollout4_thread_kernel<false><<<(int)grid, 128, 0, st>>>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, chk);
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
     case 9: return tg::launch_rollout<9, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
     case 16: return tg::launch_rollout<16, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
     }
