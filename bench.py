@@ -486,6 +486,18 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
         out["size_4x4x4"]["rollout"] = {"value": B4 * R4 / ms_r4 * 1e3, "unit": "game-steps/s", "K": R4, "ms": ms_r4,
                                         "hbm_frac": B4 * (2 * S4 ** 3 + R4 * 3 * S4 + 8) / (ms_r4 * 1e-3) / 1e9 / peak}
         del rev4
+        # batched leaf expansion at 4x4x4: four threads per parent, rows in registers, k = 7 candidate actions per state
+        nb4 = 1 << 20
+        tb4 = t4[:, :nb4].permute(1, 0, 2).contiguous()
+        k4 = tb4.shape[1]
+        moved4 = 64 * (1 + 1 / k4) + 16 + 5
+        ms_e4 = _time_ms(lambda: env.expand_children(s4[:nb4], tb4, S4, 1, with_keys=False), 5, torch)
+        ms_e4k = _time_ms(lambda: env.expand_children(s4[:nb4], tb4, S4, 1, with_keys=True), 5, torch)
+        out["size_4x4x4"]["expand_children"] = {"value": nb4 * k4 / ms_e4 * 1e3, "unit": "children/s", "k": k4, "ms": ms_e4,
+                                                "hbm_frac": nb4 * k4 * moved4 / (ms_e4 * 1e-3) / 1e9 / peak,
+                                                "with_state_keys": {"value": nb4 * k4 / ms_e4k * 1e3, "ms": ms_e4k,
+                                                                    "hbm_frac": nb4 * k4 * (moved4 + 8) / (ms_e4k * 1e-3) / 1e9 / peak}}
+        del tb4
         # sample batcher at 4x4x4 (the reference's default size): four threads per sample, rows in registers
         st4 = env.DemoStore.from_tape(t4, s4, S4, 1)
         i4 = torch.randint(0, B4 * R4, (1 << 20,), device=dev)

@@ -707,14 +707,20 @@ __global__ void __launch_bounds__(64)
 // A 4x4x4 game is 64 bytes and its three matrices 48: the whole change of basis fits the registers of one thread, exact in
 // int32 (the same ring arithmetic as basis_kernel, so the same results for any int8 input): contract c with DP4A on the
 // packed input words (Y[a][b][k'] = dp4a(T[a][b][.], C[k'][.])), then b and a with scalar matrix entries -- 64 DP4A + 512
-// IMAD per game, no shared memory, no barrier (the packed-lane kernel above needs three CTA barriers per 64 games and
-// spends its time in them: 5.9 G games/s, 0.21 of HBM).
+// IMAD per game, no CTA barrier (the packed-lane kernel above needs three CTA barriers per 64 games and spends its time
+// in them: 5.9 G games/s, 0.21 of HBM).  The 32 results of a warp are one contiguous block of the output slab: they go
+// through a warp-private stage in shared memory (thread-major in, linear out) so that every store instruction writes 512
+// contiguous bytes instead of 16-byte pieces of 32 different lines.
 template <bool OUT16>
 __global__ void __launch_bounds__(128)
     basis4_thread_kernel(const int8_t *__restrict__ slab_in, const int8_t *__restrict__ mats, long long mat_stride,
                          void *__restrict__ slab_out, uint8_t *__restrict__ flags, long long N) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    constexpr int IPG = OUT16 ? 8 : 4, PITCH = IPG * 16 + 16; // 16-byte items per game; stage pitch (conflict-free both ways)
+    __shared__ __align__(16) uint8_t s_stage[4][32 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nw0 = (long long)blockIdx.x * blockDim.x + warp * 32; // first game of the warp
+    if (nw0 >= N) return;
+    const long long n = min(nw0 + lane, N - 1); // spare lanes of the last warp repeat the last game
     const uint4 *mp = reinterpret_cast<const uint4 *>(mats + n * mat_stride);
     const uint4 mA = __ldg(mp), mB = __ldg(mp + 1), mC = __ldg(mp + 2); // row r of a matrix = word r
     const uint32_t rA[4] = {mA.x, mA.y, mA.z, mA.w}, rB[4] = {mB.x, mB.y, mB.z, mB.w}, rC[4] = {mC.x, mC.y, mC.z, mC.w};
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(128)
     }
     uint32_t bad = 0;
     if constexpr (OUT16) {
-        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(slab_out) + n * 64);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_stage[warp] + lane * PITCH);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             uint32_t w[8];
@@ -770,7 +776,7 @@ __global__ void __launch_bounds__(128)
         }
         bad >>= 16;
     } else {
-        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<int8_t *>(slab_out) + n * 64);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_stage[warp] + lane * PITCH);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             uint32_t w[4];
@@ -789,7 +795,11 @@ __global__ void __launch_bounds__(128)
         }
         bad >>= 7;
     }
-    if (flags) flags[n] = bad ? (uint8_t)TG_FLAG_RANGE : (uint8_t)0;
+    if (flags && nw0 + lane < N) flags[n] = bad ? (uint8_t)TG_FLAG_RANGE : (uint8_t)0;
+    __syncwarp();
+    const int total = (int)min(32LL, N - nw0) * IPG;
+    uint4 *out = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(slab_out) + nw0 * (IPG * 16));
+    for (int x = lane; x < total; x += 32) out[x] = *reinterpret_cast<const uint4 *>(s_stage[warp] + (x / IPG) * PITCH + (x % IPG) * 16);
 }
 
 } // namespace tg
