@@ -833,10 +833,80 @@ static int launch_demo_alias(unsigned long long first, long long N, int R, int s
     return TG_OK;
 }
 
+// ---- 4x4x4, contract v2: one THREAD per demo.  A 4x4x4 target is 16 words: it stays in the registers of the thread that
+// draws the demo's R triples one after the other (one Philox block and six table loads each) -- a term is written to the
+// tape with one coalesced 16-byte store (consecutive threads, consecutive demos of the step-major tape) and added with four
+// products v_j pack(w) and sixteen IMADs; no accumulate records in shared memory, no CTA barrier after the table copy.  The
+// 32 targets of a warp are one contiguous block of the slab: they leave through a warp-private stage so that a store
+// instruction writes 512 contiguous bytes.  Taken when R * shift^3 <= 191 (a final entry outside int8 then always decodes
+// outside [-64, 63]); larger R keeps the guarded tile kernel.
+__global__ void __launch_bounds__(128)
+    demo4_thread_kernel(unsigned long long first_demo, long long N, int R, int shift, uint8_t *__restrict__ tape, long long tape_step_stride,
+                        int8_t *__restrict__ slab, uint8_t *__restrict__ flags, const __grid_constant__ AliasDev ap) {
+    constexpr int S = 4, PITCH = 64 + 16;
+    __shared__ __align__(16) uint32_t s_alias[AliasGeo<S>::TAB_WORDS];
+    __shared__ __align__(16) uint8_t s_stage[4][32 * PITCH];
+    alias_to_smem<S, 128>(ap, s_alias);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nw0 = (long long)blockIdx.x * 128 + warp * 32; // first demo of the warp
+    if (nw0 >= N) return;
+    const bool real = nw0 + lane < N;
+    const long long n = min(nw0 + lane, N - 1);
+    const unsigned long long d = first_demo + (unsigned long long)n;
+    uint32_t acc[16]; // word 4 i + j = entries (i, j, 0..3), offset-binary
+#pragma unroll
+    for (int e = 0; e < 16; e++) acc[e] = H4;
+    const uint32_t sh4 = (uint32_t)shift * ONES4;
+    uint4 *rec = reinterpret_cast<uint4 *>(tape + n * 16);
+    const long long stride16 = tape_step_stride / 16;
+    for (int r = 0; r < R; r++) {
+        uint32_t words[3];
+        draw_triple_alias<S>(words, (uint32_t)d, (uint32_t)(d >> 32), r, ap, s_alias);
+        if (real) rec[(long long)r * stride16] = make_uint4(words[0], words[1], words[2], 0u);
+        const uint32_t cu = (words[0] + (H4 - sh4)) ^ H4, cv = (words[1] + (H4 - sh4)) ^ H4; // int8 coefficients (tokens <= 2 shift)
+        const int wi = (int)(words[2] - sh4);                                                // integer form of pack(w)
+        const int vw[4] = {coef_byte<0>(cv) * wi, coef_byte<1>(cv) * wi, coef_byte<2>(cv) * wi, coef_byte<3>(cv) * wi};
+        const int u[4] = {coef_byte<0>(cu), coef_byte<1>(cu), coef_byte<2>(cu), coef_byte<3>(cu)};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[4 * i + j] += (uint32_t)(u[i] * vw[j]);
+    }
+    // offset-binary byte in [-64, 63] + 128 <=> bits 7 and 6 differ
+    uint32_t ok = H4;
+    uint4 *mine = reinterpret_cast<uint4 *>(s_stage[warp] + lane * PITCH);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t o = acc[4 * i + j];
+            ok &= o ^ (o << 1);
+            acc[4 * i + j] = o ^ H4;
+        }
+        mine[i] = make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    }
+    if (flags && real) flags[n] = (~ok & H4) ? (uint8_t)TG_FLAG_RANGE : (uint8_t)0;
+    __syncwarp();
+    const int total = (int)min(32LL, N - nw0) * 4;
+    uint4 *out = reinterpret_cast<uint4 *>(slab + nw0 * 64);
+    for (int x = lane; x < total; x += 32) out[x] = *reinterpret_cast<const uint4 *>(s_stage[warp] + (x >> 2) * PITCH + (x & 3) * 16);
+}
+
 static int dispatch_demo_alias(unsigned long long first, long long N, int R, int S, int shift, const Categorical &cat,
                                const AliasDev &ap, uint8_t *tape, long long stride, int8_t *slab, uint8_t *flags, cudaStream_t st) {
     switch (S) {
     case 4:
+#ifdef TG_TUNING
+        if (tuning_env("TG_DEMO_VARIANT", 0) == 0)
+#endif
+        if ((long long)R * shift * shift * shift <= 191 && R <= 65535) { // one thread per demo
+            const long long grid = (N + 127) / 128;
+            if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
+            demo4_thread_kernel<<<(int)grid, 128, 0, st>>>(first, N, R, shift, tape, stride, slab, flags, ap);
+            TG_CUDA(cudaGetLastError());
+            return TG_OK;
+        }
         if (DemoCfg<4, 256, 4>::smem_bytes(R) <= 160 * 1024)
             return launch_demo_alias<4, 256, 4, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
         return launch_demo_alias<4, 256, 1, 0>(first, N, R, shift, cat, ap, tape, stride, slab, flags, st);
