@@ -840,14 +840,18 @@ static int launch_demo_alias(unsigned long long first, long long N, int R, int s
 // 32 targets of a warp are one contiguous block of the slab: they leave through a warp-private stage so that a store
 // instruction writes 512 contiguous bytes.  Taken when R * shift^3 <= 191 (a final entry outside int8 then always decodes
 // outside [-64, 63]); larger R keeps the guarded tile kernel.
+// SAMPLE = false (tg_demo_accumulate): the records come from the tape instead (any token: the guarded coefficient form).
+template <bool SAMPLE>
 __global__ void __launch_bounds__(128)
     demo4_thread_kernel(unsigned long long first_demo, long long N, int R, int shift, uint8_t *__restrict__ tape, long long tape_step_stride,
                         int8_t *__restrict__ slab, uint8_t *__restrict__ flags, const __grid_constant__ AliasDev ap) {
     constexpr int S = 4, PITCH = 64 + 16;
-    __shared__ __align__(16) uint32_t s_alias[AliasGeo<S>::TAB_WORDS];
+    __shared__ __align__(16) uint32_t s_alias[SAMPLE ? AliasGeo<S>::TAB_WORDS : 4];
     __shared__ __align__(16) uint8_t s_stage[4][32 * PITCH];
-    alias_to_smem<S, 128>(ap, s_alias);
-    __syncthreads();
+    if constexpr (SAMPLE) {
+        alias_to_smem<S, 128>(ap, s_alias);
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nw0 = (long long)blockIdx.x * 128 + warp * 32; // first demo of the warp
     if (nw0 >= N) return;
@@ -860,12 +864,20 @@ __global__ void __launch_bounds__(128)
     const uint32_t sh4 = (uint32_t)shift * ONES4;
     uint4 *rec = reinterpret_cast<uint4 *>(tape + n * 16);
     const long long stride16 = tape_step_stride / 16;
+    uint4 nextq = (!SAMPLE && R > 0) ? __ldg(reinterpret_cast<const uint4 *>(rec)) : make_uint4(0, 0, 0, 0);
     for (int r = 0; r < R; r++) {
         uint32_t words[3];
-        draw_triple_alias<S>(words, (uint32_t)d, (uint32_t)(d >> 32), r, ap, s_alias);
-        if (real) rec[(long long)r * stride16] = make_uint4(words[0], words[1], words[2], 0u);
-        const uint32_t cu = (words[0] + (H4 - sh4)) ^ H4, cv = (words[1] + (H4 - sh4)) ^ H4; // int8 coefficients (tokens <= 2 shift)
-        const int wi = (int)(words[2] - sh4);                                                // integer form of pack(w)
+        uint32_t cu, cv;
+        if constexpr (SAMPLE) {
+            draw_triple_alias<S>(words, (uint32_t)d, (uint32_t)(d >> 32), r, ap, s_alias);
+            if (real) rec[(long long)r * stride16] = make_uint4(words[0], words[1], words[2], 0u);
+            cu = (words[0] + (H4 - sh4)) ^ H4, cv = (words[1] + (H4 - sh4)) ^ H4; // int8 coefficients (tokens <= 2 shift)
+        } else {
+            words[0] = nextq.x, words[1] = nextq.y, words[2] = nextq.z;
+            if (r + 1 < R) nextq = __ldg(reinterpret_cast<const uint4 *>(rec) + (long long)(r + 1) * stride16); // next record in flight
+            cu = ((words[0] | H4) - sh4) ^ H4, cv = ((words[1] | H4) - sh4) ^ H4;
+        }
+        const int wi = (int)(words[2] - sh4); // integer form of pack(w)
         const int vw[4] = {coef_byte<0>(cv) * wi, coef_byte<1>(cv) * wi, coef_byte<2>(cv) * wi, coef_byte<3>(cv) * wi};
         const int u[4] = {coef_byte<0>(cu), coef_byte<1>(cu), coef_byte<2>(cu), coef_byte<3>(cu)};
 #pragma unroll
@@ -903,7 +915,7 @@ static int dispatch_demo_alias(unsigned long long first, long long N, int R, int
         if ((long long)R * shift * shift * shift <= 191 && R <= 65535) { // one thread per demo
             const long long grid = (N + 127) / 128;
             if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
-            demo4_thread_kernel<<<(int)grid, 128, 0, st>>>(first, N, R, shift, tape, stride, slab, flags, ap);
+            demo4_thread_kernel<true><<<(int)grid, 128, 0, st>>>(first, N, R, shift, tape, stride, slab, flags, ap);
             TG_CUDA(cudaGetLastError());
             return TG_OK;
         }
@@ -1248,6 +1260,13 @@ int tg_demo_accumulate(const uint8_t *tape, int64_t tape_step_stride, int64_t N,
 #endif
     if (S == 16 && use_mma && tg::demo_acc16_mma_applies(R))
         return tg::launch_demo_acc16_mma(tape, tape_step_stride, N, R, shift, slab, flags, 0, (cudaStream_t)stream);
+    if (S == 4 && (long long)R * shift * shift * shift <= 191 && R <= 65535 && N <= 0x7FFFFFFFLL * 128) { // one thread per demo
+        static const tg::AliasDev no_tables = {};
+        tg::demo4_thread_kernel<false><<<(int)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(0, N, R, shift, const_cast<uint8_t *>(tape),
+                                                                                              tape_step_stride, slab, flags, no_tables);
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
     tg::Categorical cat = {};
     // 9x9x9: walk only the terms with a non-zero v_j (the masks are built from the tape itself, so this is exact for any tape;
     // with the reference's distributions 70 % of the coefficients are zero: 0.62 -> 0.55 ms per 2^20 demos; a tape without zeros
