@@ -889,8 +889,8 @@ __device__ __forceinline__ uint32_t mulmod31(uint32_t a, uint32_t b) {
 template <int S>
 __global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__restrict__ ranks, long long B) {
     using G = Geo<S>;
-    constexpr int LG = S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32)); // lanes per matrix (power of two)
-    constexpr int MPW = 32 / LG;                                        // matrices per warp
+    constexpr int LG = S;       // lanes per matrix: 4 / 9 / 16 (the shuffles address absolute lanes, so any group size works)
+    constexpr int MPW = 32 / LG; // matrices per warp: 8 / 3 (lanes 27..31 idle; two per warp with groups of 16 was 1.5x slower) / 2
     constexpr uint32_t P = 0x7FFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LG, r = lane % LG;
@@ -898,7 +898,7 @@ __global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__re
     const long long mat = warp * MPW + sub; // matrix index = game * S + slice
     const long long game = mat / S;
     const int slice = (int)(mat - game * S);
-    const bool live = game < B && r < S;
+    const bool live = sub < MPW && game < B && r < S;
     uint32_t row[S];
 #pragma unroll
     for (int c = 0; c < S; c++) {
@@ -906,7 +906,7 @@ __global__ void slice_rank_kernel(const int8_t *__restrict__ slab, int32_t *__re
         if (live) v = slab[game * G::GP + slice * G::RP + r * S + c];
         row[c] = v >= 0 ? (uint32_t)v : P - (uint32_t)(-v);
     }
-    const uint32_t gmask = (LG == 32) ? 0xFFFFFFFFu : (((1u << LG) - 1u) << (sub * LG));
+    const uint32_t gmask = sub < MPW ? (((1u << LG) - 1u) << (sub * LG)) : 0u;
     bool used = !live;
     int rank = 0;
 #pragma unroll
@@ -1210,7 +1210,7 @@ int tg_slice_rank(const int8_t *slab, int32_t *ranks, int64_t B, int S, void *st
     cudaStream_t st = (cudaStream_t)stream;
     TG_CUDA(cudaMemsetAsync(ranks, 0, (size_t)B * 4, st));
     TG_SWITCH_S(S, {
-        constexpr int LG = kS <= 4 ? 4 : (kS <= 8 ? 8 : (kS <= 16 ? 16 : 32));
+        constexpr int LG = kS;
         const long long warps = (B * kS + (32 / LG) - 1) / (32 / LG);
         tg::slice_rank_kernel<kS><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(slab, ranks, B);
     });
