@@ -480,6 +480,15 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
                              "step_hbm_frac": B4 * STEP_BYTES[4] / (ms_step * 1e-3) / 1e9 / peak}
         # change of basis at 4x4x4: one thread per game, exact int32 in registers (csrc/tg_basis.cu basis4_thread_kernel)
         out["size_4x4x4"]["change_of_basis"], _ = basis_block(S4, s4, 1 << 20, 0.3)
+        # sample batcher at 4x4x4 (the reference's default size): four threads per sample, rows in registers
+        st4 = env.DemoStore.from_tape(t4, s4, S4, 1)
+        i4 = torch.randint(0, B4 * R4, (1 << 20,), device=dev)
+        ms_s4 = _time_ms(lambda: st4.samples(i4, 2, replay_shift=1), 5, torch)
+        out["size_4x4x4"]["demo_sample"] = {"value": i4.numel() / ms_s4 * 1e3, "unit": "samples/s", "ms": ms_s4, "dim_t": 2,
+                                            "samples": i4.numel(),
+                                            "hbm_frac": i4.numel() * (2 * S4 ** 3 * 4) / (ms_s4 * 1e-3) / 1e9 / peak}
+        del st4, i4
+        torch.cuda.empty_cache()  # the blocks below allocate 0.5 GB outputs of other sizes: keep the allocator's pools apart
         # fused rollout at 4x4x4: one thread per game, the game in registers for all K steps
         rev4 = t4.flip(0).contiguous()
         ms_r4 = _time_ms(lambda: env.rollout(s4, rev4, S4, 1, out=o4), 5, torch)
@@ -498,14 +507,6 @@ def measure_extras(env, dev, S, shift, slab, tape3, R, values, probs, world, ran
                                                 "with_state_keys": {"value": nb4 * k4 / ms_e4k * 1e3, "ms": ms_e4k,
                                                                     "hbm_frac": nb4 * k4 * (moved4 + 8) / (ms_e4k * 1e-3) / 1e9 / peak}}
         del tb4
-        # sample batcher at 4x4x4 (the reference's default size): four threads per sample, rows in registers
-        st4 = env.DemoStore.from_tape(t4, s4, S4, 1)
-        i4 = torch.randint(0, B4 * R4, (1 << 20,), device=dev)
-        ms_s4 = _time_ms(lambda: st4.samples(i4, 2, replay_shift=1), 5, torch)
-        out["size_4x4x4"]["demo_sample"] = {"value": i4.numel() / ms_s4 * 1e3, "unit": "samples/s", "ms": ms_s4, "dim_t": 2,
-                                            "samples": i4.numel(),
-                                            "hbm_frac": i4.numel() * (2 * S4 ** 3 * 4) / (ms_s4 * 1e-3) / 1e9 / peak}
-        del st4, i4
         del t4, s4, o4
         # BASELINE.json configs[2]: 16x16x16 demos (rank <= 49) followed by the change-of-basis augmentation, one
         # (A, B, C) triple per demo -- the one contraction that runs on the tensor cores (csrc/tg_basis_mma.cu)

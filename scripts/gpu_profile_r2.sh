@@ -15,7 +15,7 @@ python scripts/time_r2.py > gpurun_out/r02_time_r2.txt 2>&1
 python scripts/time_kernels.py > gpurun_out/r02_time_kernels.txt 2>&1
 for w in step demo9 demo4 demo16 sample basis9 basis16 basis4 rank rollout expand; do
   timeout 120 python scripts/prof_r2.py $w > /dev/null 2>&1 && \
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'step_kernel|demo_kernel|demo_sample|basis_mma|basis_fast|slice_rank|rollout_kernel|expand_kernel' -s 1 -c 1 -o gpurun_out/r02_prof_$w -f python scripts/prof_r2.py $w > gpurun_out/r02_ncu_$w.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'step_kernel|demo_kernel|demo4_thread|demo_sample|basis_mma|basis_fast|basis4_thread|slice_rank|rollout_kernel|rollout4|expand_kernel|expand4' -s 1 -c 1 -o gpurun_out/r02_prof_$w -f python scripts/prof_r2.py $w > gpurun_out/r02_ncu_$w.log 2>&1
   tail -1 gpurun_out/r02_ncu_$w.log
 done
 head -c 1200 gpurun_out/r02_bench_S9.json; echo; cat gpurun_out/r02_bench_reference_arm.json | head -c 800
