@@ -13,7 +13,7 @@
 //     run[j][m] += (-u_i v_j) * W_m ,   W_m = the three words of pack(w) in integer form,
 // i.e. one u coefficient (a byte load), nine v coefficients (three packed subtractions, nine sign-extending PRMTs), three W
 // words (two funnel shifts), nine products and 27 independent IMADs per lane -- no exchange between lanes, no shared-
-// memory traffic besides the token record, and "is the game solved" is a checksum of the 27 words plus one ballot (the warp
+// memory traffic besides the token record, and "is the game solved" is a checksum over nine of the 27 words plus one ballot (confirmed word by word when all nine rows pass) (the warp
 // owns the whole game: no shared-memory votes, no atomics, no CTA-level barrier).  Tokens stream through the same TMA ring
 // as in tg_rollout.cu; start states come in and results leave with one bulk copy per game through a per-warp stage.
 #include "tg_step.cuh"
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
     }
     __syncwarp();
     int until = chk, my_steps = 0;
-    constexpr uint32_t ZSUM = (uint32_t)(27ull * H4); // checksum of an all-zero row
+    constexpr uint32_t ZSUM = (uint32_t)(9ull * H4); // checksum (first word of every run) of an all-zero row
     const uint32_t sh4 = (uint32_t)shift * ONES4;
     const uint8_t *tok_mine = s_tok + (wg0 + (owner ? q : 0)) * TP;
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
 #pragma unroll
             for (int j = 0; j < S; j++) {
                 run[j][0] += (uint32_t)(c[j] * W0), run[j][1] += (uint32_t)(c[j] * W1), run[j][2] += (uint32_t)(c[j] * W2);
-                sum += run[j][0] + run[j][1] + run[j][2];
+                sum += run[j][0]; // a cheap necessary condition for a zero row: the first words of its nine runs
             }
             if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
                 until = chk;
