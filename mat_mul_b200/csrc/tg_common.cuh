@@ -58,9 +58,9 @@ int launch_basis_mma16(const int8_t *slab_in, const int8_t *mats, long long mat_
 int launch_basis_mma9(const int8_t *slab_in, const int8_t *mats, long long mat_stride, void *slab_out, int out16, uint8_t *flags,
                       long long N, cudaStream_t st);
 
-// tg_rollout9.cu: tg_rollout / tg_replay at 9x9x9, one thread per row of a game
-int launch_rollout_rows9(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out, uint8_t *flags,
-                         int32_t *nnz, int32_t *steps, long long B, int shift, int freeze, cudaStream_t st);
+// tg_rollout9.cu: tg_rollout / tg_replay at 9x9x9 and 16x16x16, one thread per row of a game
+int launch_rollout_rows(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out, uint8_t *flags,
+                        int32_t *nnz, int32_t *steps, long long B, int S, int shift, int freeze, cudaStream_t st);
 // tg_demo_mma.cu: sum of the R rank-1 terms of 16x16x16 action lists, one warp per demo on mma.sync f16 (R <= 64)
 bool demo_acc16_mma_applies(int R);
 int launch_demo_acc16_mma(const uint8_t *tape, long long tape_step_stride, long long N, int R, int shift, int8_t *slab,

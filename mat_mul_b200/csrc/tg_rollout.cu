@@ -348,8 +348,13 @@ static int rollout_dispatch(const int8_t *slab_in, const uint8_t *tape, int64_t 
         if (tg::tuning_env("TG_ROLLOUT_COLUMNS", 0)) // A/B: the word-column kernel of this file
             return tg::launch_rollout<9, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
 #endif
-        return tg::launch_rollout_rows9(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
-    case 16: return tg::launch_rollout<16, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+        return tg::launch_rollout_rows(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, 9, shift, freeze, st);
+    case 16:
+#ifdef TG_TUNING
+        if (tg::tuning_env("TG_ROLLOUT_COLUMNS", 0))
+            return tg::launch_rollout<16, 256, 4>(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+#endif
+        return tg::launch_rollout_rows(slab_in, tape, tape_step_stride, K, slab_out, flags, nnz, steps, B, 16, shift, freeze, st);
     }
     return TG_E_ARG;
 }

@@ -21,15 +21,30 @@
 namespace tg {
 namespace roll9 {
 
-constexpr int S = 9, RP = 84, GP = 768, TP = 32, WR = 21;
-constexpr int NW = 8, GPW = 3, TG = NW * GPW; // compute warps per CTA, games per warp, games per CTA
-constexpr int NST = 4;                        // token ring depth
-constexpr int TOK_BYTES = TG * TP;            // one ring stage: the step's records of the CTA's games
-constexpr int GPITCH = GP + 16;               // game pitch of the state stage (banks of the three games 4 words apart)
-constexpr int STAGE_BYTES = GPW * GPITCH;
-constexpr int WARP_BYTES = STAGE_BYTES + 32 * 4; // + one word per lane for the final reductions
-constexpr int SMEM_BYTES = NST * TOK_BYTES + NW * WARP_BYTES + (2 * NST + NW) * 8;
-static_assert(TOK_BYTES % 16 == 0 && WARP_BYTES % 16 == 0, "bulk-copy alignment");
+constexpr int NW = 8;  // compute warps per CTA
+constexpr int NST = 4; // token ring depth
+// 16x16x16 runs the same kernel: rows of 16 aligned runs of four words (no padding, no unpacking), 16 lanes per game, two
+// games per warp.
+template <int S_>
+struct RowGeo {
+    using G = Geo<S_>;
+    static constexpr int S = S_, RP = G::RP, GP = G::GP, TP = G::TP, WR = G::RP / 4;
+    static constexpr int KW = (S + 3) / 4;          // words per run
+    static constexpr int GPW = 32 / S, TG = NW * GPW; // games per warp, games per CTA
+    static constexpr int TOK_BYTES = TG * TP;       // one ring stage: the step's records of the CTA's games
+    // state stage of a warp: 9x9x9 games as they lie in the slab (rows 21 words apart: the nine lanes of a game hit nine
+    // banks); 16x16x16 rows are 64 words = one bank for all sixteen lanes, so every row is a bulk copy of its own to a
+    // pitch of 68 words (2-way instead of 16-way conflicts on the way in and out)
+    static constexpr bool ROWCOPY = RP % 128 == 0;
+    static constexpr int ROWPITCH = ROWCOPY ? RP + 16 : RP;
+    static constexpr int GPITCH = (ROWCOPY ? S * ROWPITCH : GP) + 16; // game pitch (banks of a warp's games 4 words apart)
+    static constexpr int STAGE_BYTES = GPW * GPITCH;
+    static constexpr int WARP_BYTES = STAGE_BYTES + 32 * 4; // + one word per lane for the final reductions
+    static constexpr int SMEM_BYTES = NST * TOK_BYTES + NW * WARP_BYTES + (2 * NST + NW) * 8;
+    static constexpr uint32_t GROUP = (1u << S) - 1u; // the lanes of one game in a ballot
+    static_assert(TOK_BYTES % 16 == 0 && WARP_BYTES % 16 == 0, "bulk-copy alignment");
+    static_assert(S == 9 || S == 16, "row-owner rollout: 9x9x9 and 16x16x16");
+};
 
 template <int B>
 __device__ __forceinline__ int sx(uint32_t w) { // sign-extended byte B
@@ -39,11 +54,14 @@ __device__ __forceinline__ int sx(uint32_t w) { // sign-extended byte B
     return (int)d;
 }
 
-template <bool FREEZE>
-__global__ void __launch_bounds__(32 * (NW + 1), 3)
-    rollout_rows9_kernel(const int8_t *__restrict__ slab_in, const uint8_t *__restrict__ tape, long long tape_step_stride, int K,
+template <int S, bool FREEZE>
+__global__ void __launch_bounds__(32 * (NW + 1), S == 9 ? 3 : 2)
+    rollout_rows_kernel(const int8_t *__restrict__ slab_in, const uint8_t *__restrict__ tape, long long tape_step_stride, int K,
                          int8_t *__restrict__ slab_out, uint8_t *__restrict__ flags, int32_t *__restrict__ nnz,
                          int32_t *__restrict__ steps, long long B, int shift, int chk) {
+    using R = RowGeo<S>;
+    constexpr int RP = R::RP, GP = R::GP, TP = R::TP, WR = R::WR, KW = R::KW, GPW = R::GPW, TG = R::TG, TOK_BYTES = R::TOK_BYTES,
+                  GPITCH = R::GPITCH, STAGE_BYTES = R::STAGE_BYTES, WARP_BYTES = R::WARP_BYTES, ROWPITCH = R::ROWPITCH;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *s_tok = smem;                                                     // [NST][TG][TP]
     uint8_t *s_warp = smem + NST * TOK_BYTES;                                  // [NW][WARP_BYTES]
@@ -80,40 +98,44 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
     uint32_t *s_red = reinterpret_cast<uint32_t *>(s_stage + STAGE_BYTES);  // [32]
     const int wg0 = warp * GPW;                                             // first game of the warp inside the CTA tile
     const int nwg = max(0, min(GPW, ng - wg0));                             // games this warp really has
-    if (lane == 0 && nwg > 0) {
-        mbar_expect_tx(&s_in[warp], (uint32_t)(nwg * GP));
-        for (int q = 0; q < nwg; q++) bulk_g2s(s_stage + q * GPITCH, slab_in + (g0 + wg0 + q) * GP, GP, &s_in[warp]);
-    }
-    const int q = lane / S, i = lane - q * S; // this lane's game and row (lanes 27..31: q == 3, idle)
+    const int q = lane / S, i = lane - q * S; // this lane's game and row (9x9x9: lanes 27..31 have q == 3 and idle)
     const bool owner = q < nwg;
+    if (lane == 0 && nwg > 0) mbar_expect_tx(&s_in[warp], (uint32_t)(nwg * GP));
+    __syncwarp();
+    if constexpr (R::ROWCOPY) {
+        if (owner) bulk_g2s(s_stage + q * GPITCH + i * ROWPITCH, slab_in + (g0 + wg0 + q) * GP + i * RP, RP, &s_in[warp]);
+    } else if (lane == 0) {
+        for (int qq = 0; qq < nwg; qq++) bulk_g2s(s_stage + qq * GPITCH, slab_in + (g0 + wg0 + qq) * GP, GP, &s_in[warp]);
+    }
 
-    uint32_t run[S][3]; // run j = entries (i, j, 0..3 | 4..7 | 8), offset-binary; bytes 1..3 of word 2 are padding (0x80)
+    uint32_t run[S][KW]; // run j = entries (i, j, 0..S-1) as packed words, offset-binary; 9x9x9: bytes 1..3 of word 2 are padding (0x80)
     uint32_t bad = 0;
     bool alive = owner;
     if (nwg > 0) mbar_wait(&s_in[warp], 0);
     {
-        uint32_t r[WR + 1];
+        uint32_t r[WR + 2];
         uint32_t nzw = 0;
         if (owner) {
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_stage + q * GPITCH + i * RP);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_stage + q * GPITCH + i * ROWPITCH);
 #pragma unroll
             for (int w = 0; w < WR; w++) r[w] = src[w];
-            r[WR - 1] &= 0x000000FFu; // entries 81..83 of a row are padding
+            if constexpr (S * S % 4 != 0) r[WR - 1] &= 0xFFFFFFFFu >> (8 * (4 - S * S % 4)); // row padding (9x9x9: entries 81..83)
         } else {
 #pragma unroll
             for (int w = 0; w < WR; w++) r[w] = 0;
         }
-        r[WR] = 0;
+        r[WR] = r[WR + 1] = 0;
 #pragma unroll
         for (int j = 0; j < S; j++) {
-            const int o = 9 * j, w0 = o >> 2, sh = 8 * (o & 3);
-            const uint32_t x0 = __funnelshift_r(r[w0], r[w0 + 1], sh), x1 = __funnelshift_r(r[w0 + 1], r[w0 + 2 <= WR ? w0 + 2 : WR], sh);
-            const int o8 = o + 8;
-            const uint32_t x2 = (r[o8 >> 2] >> (8 * (o8 & 3))) & 0xFFu;
-            nzw |= x0 | x1 | x2;
-            run[j][0] = x0 ^ H4, run[j][1] = x1 ^ H4, run[j][2] = x2 ^ H4;
+            const int o = S * j, w0 = o >> 2, sh = 8 * (o & 3); // the run starts at byte S j of the row
 #pragma unroll
-            for (int m = 0; m < 3; m++) bad |= ~(run[j][m] ^ (run[j][m] << 1)); // the start state must already be inside [-64,63]
+            for (int m = 0; m < KW; m++) {
+                uint32_t x = __funnelshift_r(r[w0 + m], r[w0 + m + 1], sh);
+                if (S - 4 * m < 4) x &= 0xFFFFFFFFu >> (8 * (4 - (S - 4 * m))); // the last word of a 9-entry run holds one entry
+                nzw |= x;
+                run[j][m] = x ^ H4;
+                bad |= ~(run[j][m] ^ (run[j][m] << 1)); // the start state must already be inside [-64,63]
+            }
         }
         s_red[lane] = nzw;
     }
@@ -126,7 +148,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
     }
     __syncwarp();
     int until = chk, my_steps = 0;
-    constexpr uint32_t ZSUM = (uint32_t)(9ull * H4); // checksum (first word of every run) of an all-zero row
+    constexpr uint32_t ZSUM = (uint32_t)((unsigned long long)S * H4); // checksum (first word of every run) of an all-zero row
     const uint32_t sh4 = (uint32_t)shift * ONES4;
     const uint8_t *tok_mine = s_tok + (wg0 + (owner ? q : 0)) * TP;
 
@@ -135,26 +157,38 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
         bool zero_row = true;
         if (alive) {
             const uint8_t *tok = tok_mine + st * TOK_BYTES;
-            const uint4 qa = *reinterpret_cast<const uint4 *>(tok), qb = *reinterpret_cast<const uint4 *>(tok + 16);
             const int nu = shift - (int)tok[i]; // -u_i
-            // v = bytes 9..17, w = bytes 18..26 of the record
-            const uint32_t cv2 = ((qa.z | H4) - sh4) ^ H4, cv3 = ((qa.w | H4) - sh4) ^ H4, cv4 = ((qb.x | H4) - sh4) ^ H4;
-            const int c[S] = {nu * sx<1>(cv2), nu * sx<2>(cv2), nu * sx<3>(cv2), nu * sx<0>(cv3), nu * sx<1>(cv3),
-                              nu * sx<2>(cv3), nu * sx<3>(cv3), nu * sx<0>(cv4), nu * sx<1>(cv4)};
-            const int W0 = (int)(__funnelshift_r(qb.x, qb.y, 16) - sh4), W1 = (int)(__funnelshift_r(qb.y, qb.z, 16) - sh4);
-            const int W2 = (int)((qb.z >> 16) & 0xFFu) - shift;
+            int c[S], W[KW];                    // -u_i v_j; pack(w) in integer form
+            if constexpr (S == 9) { // v = bytes 9..17, w = bytes 18..26 of the record
+                const uint4 qa = *reinterpret_cast<const uint4 *>(tok), qb = *reinterpret_cast<const uint4 *>(tok + 16);
+                const uint32_t cv2 = ((qa.z | H4) - sh4) ^ H4, cv3 = ((qa.w | H4) - sh4) ^ H4, cv4 = ((qb.x | H4) - sh4) ^ H4;
+                c[0] = nu * sx<1>(cv2), c[1] = nu * sx<2>(cv2), c[2] = nu * sx<3>(cv2), c[3] = nu * sx<0>(cv3), c[4] = nu * sx<1>(cv3);
+                c[5] = nu * sx<2>(cv3), c[6] = nu * sx<3>(cv3), c[7] = nu * sx<0>(cv4), c[8] = nu * sx<1>(cv4);
+                W[0] = (int)(__funnelshift_r(qb.x, qb.y, 16) - sh4), W[1] = (int)(__funnelshift_r(qb.y, qb.z, 16) - sh4);
+                W[2] = (int)((qb.z >> 16) & 0xFFu) - shift;
+            } else { // v = bytes 16..31, w = bytes 32..47
+                const uint4 qv = *reinterpret_cast<const uint4 *>(tok + 16), qw = *reinterpret_cast<const uint4 *>(tok + 32);
+                const uint32_t vw[4] = {qv.x, qv.y, qv.z, qv.w}, ww[4] = {qw.x, qw.y, qw.z, qw.w};
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const uint32_t cv = ((vw[m] | H4) - sh4) ^ H4;
+                    c[4 * m] = nu * sx<0>(cv), c[4 * m + 1] = nu * sx<1>(cv), c[4 * m + 2] = nu * sx<2>(cv), c[4 * m + 3] = nu * sx<3>(cv);
+                    W[m] = (int)(ww[m] - sh4);
+                }
+            }
             uint32_t sum = 0;
 #pragma unroll
             for (int j = 0; j < S; j++) {
-                run[j][0] += (uint32_t)(c[j] * W0), run[j][1] += (uint32_t)(c[j] * W1), run[j][2] += (uint32_t)(c[j] * W2);
-                sum += run[j][0]; // a cheap necessary condition for a zero row: the first words of its nine runs
+#pragma unroll
+                for (int m = 0; m < KW; m++) run[j][m] += (uint32_t)(c[j] * W[m]);
+                sum += run[j][0]; // a cheap necessary condition for a zero row: the first words of its runs
             }
             if (--until == 0) { // all entries still in [-64,63]? then chk more steps cannot alias the packed form
                 until = chk;
 #pragma unroll
                 for (int j = 0; j < S; j++)
 #pragma unroll
-                    for (int m = 0; m < 3; m++) bad |= ~(run[j][m] ^ (run[j][m] << 1));
+                    for (int m = 0; m < KW; m++) bad |= ~(run[j][m] ^ (run[j][m] << 1));
             }
             if (i < TP / 4) { // tape contract (tg_step.cuh): every token <= 2 * shift, else the packed update may have aliased
                 const uint32_t x = reinterpret_cast<const uint32_t *>(tok)[i];
@@ -165,15 +199,15 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
         }
         if (FREEZE) {
             uint32_t m = __ballot_sync(0xFFFFFFFFu, zero_row);
-            bool solved = alive && ((m >> (S * q)) & 0x1FFu) == 0x1FFu;
+            bool solved = alive && ((m >> (S * q)) & R::GROUP) == R::GROUP;
             if (__any_sync(0xFFFFFFFFu, solved)) { // rare: every row of a game has the zero checksum -- compare word by word
                 bool exact = true;
 #pragma unroll
                 for (int j = 0; j < S; j++)
 #pragma unroll
-                    for (int mm = 0; mm < 3; mm++) exact = exact && run[j][mm] == H4;
+                    for (int mm = 0; mm < KW; mm++) exact = exact && run[j][mm] == H4;
                 m = __ballot_sync(0xFFFFFFFFu, !alive || exact);
-                solved = alive && ((m >> (S * q)) & 0x1FFu) == 0x1FFu;
+                solved = alive && ((m >> (S * q)) & R::GROUP) == R::GROUP;
             }
             if (solved) alive = false; // solved by this step: frozen at the zero tensor
         }
@@ -194,12 +228,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
 #pragma unroll
         for (int j = 0; j < S; j++)
 #pragma unroll
-            for (int m = 0; m < 3; m++) {
+            for (int m = 0; m < KW; m++) {
                 bad |= ~(run[j][m] ^ (run[j][m] << 1));
                 run[j][m] ^= H4; // two's complement bytes (padding bytes of word 2: zero)
                 cnt += (uint32_t)__popc(nonzero_mask(run[j][m]));
             }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_stage + q * GPITCH + i * RP);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_stage + q * GPITCH + i * ROWPITCH);
 #pragma unroll
         for (int w = 0; w < WR; w++) {
             uint32_t word = 0;
@@ -210,9 +244,12 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
             }
             dst[w] = word;
         }
-        if (i == 0) { // game padding (bytes 756..767) stays zero
-            uint32_t *pad = reinterpret_cast<uint32_t *>(s_stage + q * GPITCH + S * RP);
-            pad[0] = pad[1] = pad[2] = 0u;
+        if constexpr (GP > S * RP) {
+            if (i == 0) { // game padding (9x9x9: bytes 756..767) stays zero
+                uint32_t *pad = reinterpret_cast<uint32_t *>(s_stage + q * GPITCH + S * RP);
+#pragma unroll
+                for (int x = 0; x < (GP - S * RP) / 4; x++) pad[x] = 0u;
+            }
         }
     }
     s_red[lane] = cnt;
@@ -224,11 +261,17 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
 #pragma unroll
         for (int rr = 0; rr < S; rr++) total += s_red[q * S + rr];
         const long long gidx = g0 + wg0 + q;
-        flags[gidx] = (uint8_t)((total == 0 ? TG_FLAG_TERMINAL : 0u) | (((badm >> (S * q)) & 0x1FFu) != 0 ? TG_FLAG_RANGE : 0u));
+        flags[gidx] = (uint8_t)((total == 0 ? TG_FLAG_TERMINAL : 0u) | (((badm >> (S * q)) & R::GROUP) != 0 ? TG_FLAG_RANGE : 0u));
         nnz[gidx] = (int32_t)total;
         if (steps) steps[gidx] = my_steps;
     }
-    if (lane == 0 && nwg > 0) {
+    if constexpr (R::ROWCOPY) {
+        if (owner) {
+            bulk_s2g(slab_out + (g0 + wg0 + q) * GP + i * RP, s_stage + q * GPITCH + i * ROWPITCH, RP);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else if (lane == 0 && nwg > 0) {
         for (int qq = 0; qq < nwg; qq++) bulk_s2g(slab_out + (g0 + wg0 + qq) * GP, s_stage + qq * GPITCH, GP);
         bulk_commit();
         bulk_wait_read<0>();
@@ -237,24 +280,32 @@ __global__ void __launch_bounds__(32 * (NW + 1), 3)
 
 } // namespace roll9
 
-int launch_rollout_rows9(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out, uint8_t *flags,
-                         int32_t *nnz, int32_t *steps, long long B, int shift, int freeze, cudaStream_t st) {
-    using namespace roll9;
-    const long long grid = (B + TG - 1) / TG;
+template <int S>
+static int launch_rows(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out, uint8_t *flags,
+                       int32_t *nnz, int32_t *steps, long long B, int shift, int freeze, cudaStream_t st) {
+    using R = roll9::RowGeo<S>;
+    const long long grid = (B + R::TG - 1) / R::TG;
     if (grid > 0x7FFFFFFFLL) return TG_E_ARG;
     const int s3 = shift * shift * shift;
     const int chk = s3 >= 64 ? 1 : 64 / s3;
     if (freeze) {
-        auto kern = rollout_rows9_kernel<true>;
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        kern<<<(int)grid, 32 * (NW + 1), SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B, shift, chk);
+        auto kern = roll9::rollout_rows_kernel<S, true>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES));
+        kern<<<(int)grid, 32 * (roll9::NW + 1), R::SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B, shift, chk);
     } else {
-        auto kern = rollout_rows9_kernel<false>;
-        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        kern<<<(int)grid, 32 * (NW + 1), SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B, shift, chk);
+        auto kern = roll9::rollout_rows_kernel<S, false>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R::SMEM_BYTES));
+        kern<<<(int)grid, 32 * (roll9::NW + 1), R::SMEM_BYTES, st>>>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B, shift, chk);
     }
     TG_CUDA(cudaGetLastError());
     return TG_OK;
+}
+
+int launch_rollout_rows(const int8_t *slab_in, const uint8_t *tape, long long stride, int K, int8_t *slab_out, uint8_t *flags,
+                        int32_t *nnz, int32_t *steps, long long B, int S, int shift, int freeze, cudaStream_t st) {
+    if (S == 9) return launch_rows<9>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+    if (S == 16) return launch_rows<16>(slab_in, tape, stride, K, slab_out, flags, nnz, steps, B, shift, freeze, st);
+    return TG_E_ARG;
 }
 
 } // namespace tg
