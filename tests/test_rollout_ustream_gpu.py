@@ -47,6 +47,32 @@ def test_rollout_matches_oracle(env, S, R, values, probs, shift, N, extra):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("S", [4, 9, 16])
+def test_rollout_and_replay_ragged_batches(env, S):
+    """Batches that do not fill a warp / a CTA tile of the row-owner kernels (three or two games per warp, 24 or 16 per CTA)
+    and step counts around the ring depth: tg_rollout against the oracle, tg_replay against K single tg_step launches."""
+    shift, R = 2, 6
+    rng = np.random.default_rng(300 + S)
+    for B in (1, 2, 3, 4, 23, 24, 25, 49):
+        for K in (1, 3, 4, 5, 9):
+            tok, tgt, _ = orc.demos_seeded(7 + B + K, V5, P5, R, S, shift, B)
+            tape_tok = np.concatenate([tok[:, ::-1], rng.integers(0, 2 * shift + 1, (B, 4, 3 * S))], axis=1)[:, :K]
+            want, wflags, wnnz, wsteps = orc.rollout_batch(tgt, tape_tok, shift)
+            ok = np.abs(want.reshape(B, -1)).max(1) <= 63
+            slab = torch.from_numpy(dense_to_slab(tgt)).cuda()
+            tape = torch.from_numpy(tokens_to_tape3(tape_tok)).cuda()
+            out, flags, nnz, steps = env.rollout(slab, tape, S, shift)
+            assert np.array_equal(slab_to_dense(out.cpu().numpy(), S)[ok], want[ok]), (B, K)
+            assert np.array_equal(steps.cpu().numpy()[ok], wsteps[ok]) and np.array_equal(nnz.cpu().numpy()[ok], wnnz[ok]), (B, K)
+            assert np.array_equal(flags.cpu().numpy()[ok] & 1, wflags[ok] & 1), (B, K)
+            rep, rflags, rnnz = env.replay(slab, tape, S, shift)
+            cur = slab
+            for t in range(K):
+                cur, sf, sn = env.step_batch(cur, tape[t], S, shift)
+            assert torch.equal(rep, cur) and torch.equal(rnnz, sn), (B, K)
+            assert torch.equal(rflags & 1, sf & 1), (B, K)
+
+
 def test_rollout_zero_steps_and_empty(env):
     S, shift = 9, 2
     lay = env.layout(S)
