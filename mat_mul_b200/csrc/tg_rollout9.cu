@@ -16,6 +16,7 @@
 // memory traffic besides the token record, and "is the game solved" is a checksum over nine of the 27 words plus one ballot (confirmed word by word when all nine rows pass) (the warp
 // owns the whole game: no shared-memory votes, no atomics, no CTA-level barrier).  Tokens stream through the same TMA ring
 // as in tg_rollout.cu; start states come in and results leave with one bulk copy per game through a per-warp stage.
+#include "tg_rows.cuh"
 #include "tg_step.cuh"
 
 namespace tg {
@@ -119,24 +120,19 @@ __global__ void __launch_bounds__(32 * (NW + 1), S == 9 ? 3 : 2)
             const uint32_t *src = reinterpret_cast<const uint32_t *>(s_stage + q * GPITCH + i * ROWPITCH);
 #pragma unroll
             for (int w = 0; w < WR; w++) r[w] = src[w];
-            if constexpr (S * S % 4 != 0) r[WR - 1] &= 0xFFFFFFFFu >> (8 * (4 - S * S % 4)); // row padding (9x9x9: entries 81..83)
         } else {
 #pragma unroll
             for (int w = 0; w < WR; w++) r[w] = 0;
         }
-        r[WR] = r[WR + 1] = 0;
+        unpack_row<S>(r, run);
 #pragma unroll
-        for (int j = 0; j < S; j++) {
-            const int o = S * j, w0 = o >> 2, sh = 8 * (o & 3); // the run starts at byte S j of the row
+        for (int j = 0; j < S; j++)
 #pragma unroll
             for (int m = 0; m < KW; m++) {
-                uint32_t x = __funnelshift_r(r[w0 + m], r[w0 + m + 1], sh);
-                if (S - 4 * m < 4) x &= 0xFFFFFFFFu >> (8 * (4 - (S - 4 * m))); // the last word of a 9-entry run holds one entry
-                nzw |= x;
-                run[j][m] = x ^ H4;
+                nzw |= run[j][m];
+                run[j][m] ^= H4;
                 bad |= ~(run[j][m] ^ (run[j][m] << 1)); // the start state must already be inside [-64,63]
             }
-        }
         s_red[lane] = nzw;
     }
     __syncwarp();
@@ -234,16 +230,10 @@ __global__ void __launch_bounds__(32 * (NW + 1), S == 9 ? 3 : 2)
                 cnt += (uint32_t)__popc(nonzero_mask(run[j][m]));
             }
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_stage + q * GPITCH + i * ROWPITCH);
+        uint32_t words[WR];
+        pack_row<S>(run, words);
 #pragma unroll
-        for (int w = 0; w < WR; w++) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int p = 4 * w + b; // entry (j, k) = (p / 9, p % 9) of the row; 81..83: padding
-                if (p < S * S) word |= ((run[p / S][(p % S) >> 2] >> (8 * ((p % S) & 3))) & 0xFFu) << (8 * b);
-            }
-            dst[w] = word;
-        }
+        for (int w = 0; w < WR; w++) dst[w] = words[w];
         if constexpr (GP > S * RP) {
             if (i == 0) { // game padding (9x9x9: bytes 756..767) stays zero
                 uint32_t *pad = reinterpret_cast<uint32_t *>(s_stage + q * GPITCH + S * RP);
