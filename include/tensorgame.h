@@ -12,7 +12,13 @@
  *   - plain pointers and sizes only; no torch types.
  *   - unless the name ends in _host, every pointer is a CUDA DEVICE pointer
  *     owned by the caller; calls are asynchronous on `stream` (a cudaStream_t
- *     passed as void*), never allocate and never synchronise.
+ *     passed as void*), never allocate and never synchronise -- with one
+ *     exception: tg_demo_gen_philox keeps the device form of up to eight
+ *     alias-table sets per device in static device memory (uploaded on
+ *     `stream` the first time a distribution is used; launches on other
+ *     streams wait for that upload by event); a NINTH distinct distribution
+ *     evicts one after a cudaDeviceSynchronize.  tg_demo_sample_dm (9x9x9)
+ *     zeroes a per-launch work counter in static device memory on `stream`.
  *   - *_host entry points take HOST pointers (pinned for full speed), move the
  *     data themselves through a caller-created tg_host_ctx and return after
  *     the results are in host memory.
